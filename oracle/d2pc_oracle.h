@@ -1,0 +1,146 @@
+/*
+ * d2pc_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * A dependency-free plain-C restatement of the per-frame hot path of
+ * PX4/disparity_to_point_cloud.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library, and
+ * only as the checker / the CPU baseline -- never on the product path.
+ *
+ * Parity pin: the reference has NO tests, fixtures or golden vectors
+ * (CMakeLists.txt:206-217 has the gtest stanza commented out) and cannot be
+ * compiled here (needs ROS1, cv_bridge, OpenCV C++ and PCL, none installed).
+ * The arithmetic lives in un-vendored, un-pinned third-party libraries
+ * (package.xml:41-55).  This oracle is therefore pinned against Python
+ * cv2 4.13.0 (the same OpenCV entry points the reference calls, driven with
+ * the reference's arguments): tests/golden/make_golden.py generates the
+ * committed fixtures, tests/test_oracle_*.py replay them.  PCL / ROS message
+ * semantics are restated from their public definitions (unpinned).
+ *
+ * All file:line citations are relative to /root/reference.
+ */
+#ifndef D2PC_ORACLE_H_
+#define D2PC_ORACLE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* include/disparity_to_point_cloud/disparity_to_point_cloud.hpp:90-104
+ * cv::stereoRectify(K, 0, K, 0, Size(rect_w, rect_h), I, (-baseline,0,0)) -> Q
+ * restated for that degenerate call (zero distortion, R = I, horizontal rig,
+ * CALIB_ZERO_DISPARITY, alpha = -1). q is row-major 4x4. */
+int d2pc_oracle_q_from_intrinsics(double fx, double fy, double cx, double cy,
+                                  double baseline, int rect_w, int rect_h,
+                                  double q[16]);
+
+/* src/disparity_to_point_cloud.cpp:55-57 and src/depth_map_fusion.cpp:124
+ * cv::medianBlur(src, dst, ksize) on CV_8UC1, replicate border. ksize odd.
+ * dst must not alias src. */
+void d2pc_oracle_median_blur_u8(const uint8_t *src, int w, int h,
+                                size_t src_step, uint8_t *dst, size_t dst_step,
+                                int ksize);
+
+/* src/disparity_to_point_cloud.cpp:60-61  Mat::convertTo(CV_32FC1, alpha) */
+void d2pc_oracle_convert_u8_f32(const uint8_t *src, int w, int h,
+                                size_t src_step, float *dst, size_t dst_step,
+                                double alpha);
+
+/* src/disparity_to_point_cloud.cpp:63-64
+ * cv::reprojectImageTo3D(disp, out, Q, handleMissingValues=false), CV_32F in,
+ * CV_32FC3 out (dense, 3*w floats per row).  Rounding per SURVEY.md A.2. */
+void d2pc_oracle_reproject_image_to_3d(const float *disp, int w, int h,
+                                       size_t disp_step, const double q[16],
+                                       float *xyz);
+
+/* src/disparity_to_point_cloud.cpp:69-85: border crop loop with push_back of
+ * pcl::PointXYZ {x,y,z,1.0f} into an un-reserved growing vector, then the
+ * pcl::toROSMsg memcpy into cloud.  Returns the point count
+ * max(0,w-2*border)*max(0,h-2*border).  cloud may be NULL to query the count. */
+size_t d2pc_oracle_crop_pack(const float *xyz, int w, int h, int border,
+                             uint8_t *cloud);
+
+/* src/disparity_to_point_cloud.cpp:46-92, all stages with the reference's
+ * intermediate buffers: mono8 copy -> median 11 -> x(1/8) -> reproject ->
+ * crop 40 -> pack.  Returns the point count; cloud holds count*16 bytes. */
+size_t d2pc_oracle_disparity_cb_mono8(const uint8_t *img, int w, int h,
+                                      size_t step, const double q[16],
+                                      uint8_t *cloud);
+
+/* The same callback entered after convertTo (:63 onwards): the float-entry
+ * path BASELINE.json's configs 1, 3 and 4 are quoted on. */
+size_t d2pc_oracle_disparity_cb_f32(const float *disp, int w, int h,
+                                    size_t step, const double q[16],
+                                    uint8_t *cloud);
+
+/* Extension mode CROP_FINITE: the crop output filtered
+ * by isfinite(x) && isfinite(y) && isfinite(z), order preserved. */
+size_t d2pc_oracle_filter_finite(const uint8_t *cloud, size_t n_points,
+                                 uint8_t *out);
+
+/* ROS1 wire image of the sensor_msgs/PointCloud2 the node publishes
+ * (src/disparity_to_point_cloud.cpp:79-90; layout SURVEY.md A.3).
+ * Returns bytes needed; writes only if cap is large enough. */
+size_t d2pc_oracle_serialize_pointcloud2(uint32_t seq, uint32_t sec,
+                                         uint32_t nsec, const char *frame_id,
+                                         const uint8_t *points,
+                                         uint32_t n_points, uint8_t is_dense,
+                                         uint8_t *out, size_t cap);
+
+/* ---- depth_map_fusion ---- */
+
+/* src/depth_map_fusion.cpp:247-265 cropToSquare; member_offset_y is the
+ * class member offset_y_ the function reads instead of its parameter (:252).
+ * rect = {x, y, w, h}. Returns 0, or -1 if the rectangle leaves the image
+ * (where cv::Mat::operator() would throw). */
+int d2pc_oracle_crop_to_square(int cols, int rows, int offset_x, int offset_y,
+                               int member_offset_y, int rect[4]);
+
+/* src/depth_map_fusion.cpp:268-273 rotateMat: 90 degrees clockwise.
+ * src is w x h, dst is h x w (cols = h), dense. */
+void d2pc_oracle_rotate_cw(const uint8_t *src, int w, int h, size_t src_step,
+                           uint8_t *dst);
+
+/* src/depth_map_fusion.cpp:219-235 gradFilter. */
+int d2pc_oracle_grad_filter(int dist1, int dist2, int score1, int score2,
+                            int grad1, int grad2);
+
+/* src/depth_map_fusion.cpp:162-217, the alternate (unused) fusion rules,
+ * selected by mode: 0 gradFilter, 1 maxDist, 2 maxDistUnlessBlack,
+ * 3 betterScore, 4 onlyGood1, 5 onlyGoodAvg, 6 overlap, 7 blackToWhite. */
+int d2pc_oracle_fuse_rule(int mode, int dist1, int dist2, int score1,
+                          int score2);
+
+/* One pass of DisparityCb1 + DisparityCb2 + publishFusedDepthMap
+ * (src/depth_map_fusion.cpp:46-62, 103-136) on four same-sized mono8 images:
+ * d1, s1 cropped with (+ox,+oy); d2, s2 rotated then cropped with (-ox,-oy);
+ * the merge loop; medianBlur 3 on the output container (the un-rotated d2
+ * frame cropped with (0,0)); cropMat(0,40,30,10).
+ * s1/s2 are the already-preprocessed score images (the caches
+ * cropped_score_{1,2}_ == cropped_score_{1,2}_grad_, :77, :96) at full frame
+ * size, i.e. score preprocessing is outside this function.
+ * fused: out_w x out_h bytes (dense); combined: n x n bytes (dense) -- the
+ * aliased cropped_score_combined_/cropped_score_1_ buffer after the loop.
+ * dims = {n, out_w, out_h}.  Returns 0, -1 bad geometry. */
+int d2pc_oracle_fuse(const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
+                     const uint8_t *s2, int w, int h, size_t step,
+                     int offset_x, int offset_y, int mode, uint8_t *fused,
+                     uint8_t *combined, int dims[3]);
+
+/* ---- CPU baseline helpers (bench.py cpu_baseline / --impl reference) ---- */
+
+/* Runs d2pc_oracle_disparity_cb_f32 (mono8 == 0) or _mono8 (mono8 != 0) over
+ * n_frames frames laid out back to back (frame stride = step*h bytes), frame
+ * parallel on n_threads pthreads; every frame writes its cloud to
+ * cloud + i*cloud_stride.  Returns total points. */
+size_t d2pc_oracle_run_frames(const void *frames, int n_frames, int w, int h,
+                              size_t step, int mono8, const double q[16],
+                              uint8_t *cloud, size_t cloud_stride,
+                              int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2PC_ORACLE_H_ */
