@@ -1,0 +1,364 @@
+"""disparity_to_point_cloud_b200 -- thin ctypes binding of libd2pc_b200.so.
+
+The product is the C-ABI shared library (include/d2pc_b200.h) and the C++ host
+mirror above it (csrc/node.hpp); this module only exists so that tests/ and
+bench.py can drive the C ABI from Python.  It never computes anything itself
+and never imports the CPU oracle: if the CUDA library is missing or no B200 is
+present, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libd2pc_b200.so")
+
+FILTER_CROP, FILTER_CROP_FINITE = 0, 1
+ARITH_EXACT, ARITH_FAST = 0, 1
+
+
+class D2pcError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        msg = f"{where}: {_strerror(status)} ({status})"
+        if detail:
+            msg += f" [{detail}]"
+        super().__init__(msg)
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("baseline", C.c_double),
+        ("rect_width", C.c_int32), ("rect_height", C.c_int32),
+        ("border", C.c_int32), ("median_ksize", C.c_int32), ("disparity_scale", C.c_float),
+        ("filter_mode", C.c_int32), ("arith_mode", C.c_int32),
+        ("frame_id", C.c_char * 64), ("verbose", C.c_int32),
+        ("offset_x", C.c_int32), ("offset_y", C.c_int32), ("fuse_rule", C.c_int32), ("fuse_median_ksize", C.c_int32),
+        ("fuse_crop_left", C.c_int32), ("fuse_crop_right", C.c_int32), ("fuse_crop_top", C.c_int32),
+        ("fuse_crop_bottom", C.c_int32),
+        ("max_width", C.c_int32), ("max_height", C.c_int32), ("max_batch", C.c_int32), ("n_slots", C.c_int32),
+    ]
+
+
+class PointField(C.Structure):
+    _fields_ = [("name", C.c_char * 8), ("offset", C.c_uint32), ("datatype", C.c_uint8), ("count", C.c_uint32)]
+
+
+class Cloud(C.Structure):
+    _fields_ = [
+        ("data", C.POINTER(C.c_uint8)), ("height", C.c_uint32), ("width", C.c_uint32), ("point_step", C.c_uint32),
+        ("row_step", C.c_uint32), ("is_bigendian", C.c_uint8), ("is_dense", C.c_uint8), ("n_fields", C.c_uint32),
+        ("fields", PointField * 3),
+    ]
+
+    def bytes_view(self) -> np.ndarray:
+        n = self.row_step * self.height
+        if n == 0:
+            return np.empty(0, dtype=np.uint8)
+        return np.ctypeslib.as_array(self.data, shape=(n,))
+
+
+class Image(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_uint8)), ("width", C.c_uint32), ("height", C.c_uint32), ("step", C.c_uint32)]
+
+    def array(self) -> np.ndarray:
+        a = np.ctypeslib.as_array(self.data, shape=(self.height, self.step))
+        return a[:, : self.width]
+
+
+CLOUD_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.POINTER(Cloud))
+
+# every symbol include/d2pc_b200.h declares: (name, restype, argtypes)
+_u8p, _f32p, _f64p, _i32p, _u32p = (C.POINTER(t) for t in (C.c_uint8, C.c_float, C.c_double, C.c_int, C.c_uint32))
+_ctx = C.c_void_p
+SYMBOLS = [
+    ("d2pc_config_default", None, [C.POINTER(Config)]),
+    ("d2pc_create", C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(_ctx)]),
+    ("d2pc_destroy", None, [_ctx]),
+    ("d2pc_q_from_intrinsics", C.c_int, [C.c_double] * 5 + [C.c_int, C.c_int, _f64p]),
+    ("d2pc_set_q", C.c_int, [_ctx, _f64p]),
+    ("d2pc_get_q", C.c_int, [_ctx, _f64p]),
+    ("d2pc_set_filter_mode", C.c_int, [_ctx, C.c_int]),
+    ("d2pc_set_arith_mode", C.c_int, [_ctx, C.c_int]),
+    ("d2pc_process_mono8", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Cloud)]),
+    ("d2pc_process_f32", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Cloud)]),
+    ("d2pc_submit_mono8", C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    ("d2pc_submit_f32", C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    ("d2pc_wait", C.c_int, [_ctx, C.c_int, C.POINTER(Cloud)]),
+    ("d2pc_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    ("d2pc_host_free", C.c_int, [C.c_void_p]),
+    ("d2pc_process_stream", C.c_int, [_ctx, C.c_void_p, C.c_uint64, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32,
+                                      C.c_uint32, C.c_uint32, CLOUD_SINK, C.c_void_p]),
+    ("d2pc_reproject_f32_device", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t,
+                                            C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("d2pc_reproject_mono8_device", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t,
+                                              C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("d2pc_median_u8_device", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p,
+                                        C.c_size_t, C.c_int]),
+    ("d2pc_compute_stream", C.c_void_p, [_ctx]),
+    ("d2pc_sync", C.c_int, [_ctx]),
+    ("d2pc_launch_count", C.c_uint64, [_ctx]),
+    ("d2pc_fuse_geometry", C.c_int, [_ctx, C.c_uint32, C.c_uint32, _i32p, _i32p, _i32p, _i32p]),
+    ("d2pc_fuse", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                            C.c_uint32, C.POINTER(Image), C.POINTER(Image)]),
+    ("d2pc_fuse_device", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                   C.c_size_t, C.c_void_p, C.c_void_p]),
+    ("d2pc_fuse_then_process", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                         C.c_uint32, C.c_uint32, C.POINTER(Cloud)]),
+    ("d2pc_serialize_pointcloud2", C.c_size_t, [_ctx, C.POINTER(Cloud), C.c_uint32, C.c_uint32, C.c_uint32,
+                                                C.c_void_p, C.c_size_t]),
+    ("d2pc_set_tuning", C.c_int, [_ctx, C.c_char_p, C.c_int]),
+    ("d2pc_strerror", C.c_char_p, [C.c_int]),
+    ("d2pc_last_cuda_error", C.c_char_p, [_ctx]),
+    ("d2pc_abi_version", C.c_int, []),
+    ("d2pc_device_count", C.c_int, []),
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads libd2pc_b200.so.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: build it with `python -m disparity_to_point_cloud_b200.build` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _strerror(status: int) -> str:
+    try:
+        return lib().d2pc_strerror(status).decode()
+    except Exception:  # pragma: no cover
+        return "?"
+
+
+def default_config() -> Config:
+    c = Config()
+    lib().d2pc_config_default(C.byref(c))
+    return c
+
+
+def q_from_intrinsics(fx=714.24, fy=713.5, cx=376.0, cy=240.0, baseline=0.09, rect_w=752, rect_h=480) -> np.ndarray:
+    q = np.zeros(16, dtype=np.float64)
+    rc = lib().d2pc_q_from_intrinsics(fx, fy, cx, cy, baseline, rect_w, rect_h, q.ctypes.data_as(_f64p))
+    if rc:
+        raise D2pcError(rc, "d2pc_q_from_intrinsics")
+    return q.reshape(4, 4)
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (d2pc_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._ptr = C.c_void_p()
+        rc = lib().d2pc_host_alloc(C.byref(self._ptr), max(n, 1))
+        if rc:
+            raise D2pcError(rc, "d2pc_host_alloc")
+        buf = (C.c_uint8 * max(n, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            lib().d2pc_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One d2pc_ctx: the GPU stand-in for a Disparity2PCloud / DepthMapFusion node object."""
+
+    def __init__(self, device: int = 0, config: Config | None = None, **overrides):
+        cfg = config or default_config()
+        for k, v in overrides.items():
+            if k == "frame_id":
+                v = v.encode() if isinstance(v, str) else v
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self._h = _ctx()
+        rc = lib().d2pc_create(C.byref(cfg), device, C.byref(self._h))
+        if rc:
+            raise D2pcError(rc, "d2pc_create")
+        self._keep = []
+
+    # -- lifecycle
+    def close(self):
+        if self._h:
+            lib().d2pc_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, where):
+        if rc:
+            raise D2pcError(rc, where, lib().d2pc_last_cuda_error(self._h).decode())
+
+    # -- parameters
+    def set_q(self, q):
+        q = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(16))
+        self._check(lib().d2pc_set_q(self._h, q.ctypes.data_as(_f64p)), "d2pc_set_q")
+
+    def get_q(self) -> np.ndarray:
+        q = np.zeros(16, dtype=np.float64)
+        self._check(lib().d2pc_get_q(self._h, q.ctypes.data_as(_f64p)), "d2pc_get_q")
+        return q.reshape(4, 4)
+
+    def set_filter_mode(self, m):
+        self._check(lib().d2pc_set_filter_mode(self._h, m), "d2pc_set_filter_mode")
+
+    def set_arith_mode(self, m):
+        self._check(lib().d2pc_set_arith_mode(self._h, m), "d2pc_set_arith_mode")
+
+    def set_tuning(self, key: str, value: int):
+        self._check(lib().d2pc_set_tuning(self._h, key.encode(), int(value)), f"d2pc_set_tuning({key})")
+
+    # -- host entry points (what DisparityCb does)
+    @staticmethod
+    def _frame(img, dtype):
+        a = np.asarray(img)
+        if a.dtype != dtype or a.ndim != 2 or a.strides[1] != a.itemsize:
+            a = np.ascontiguousarray(a, dtype=dtype)
+        return a
+
+    def process_mono8(self, img) -> np.ndarray:
+        a = self._frame(img, np.uint8)
+        cl = Cloud()
+        self._check(lib().d2pc_process_mono8(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0],
+                                             C.byref(cl)), "d2pc_process_mono8")
+        self.last_cloud = cl
+        return cl.bytes_view().copy()
+
+    def process_f32(self, disp) -> np.ndarray:
+        a = self._frame(disp, np.float32)
+        cl = Cloud()
+        self._check(lib().d2pc_process_f32(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0],
+                                           C.byref(cl)), "d2pc_process_f32")
+        self.last_cloud = cl
+        return cl.bytes_view().copy()
+
+    def submit(self, slot: int, frame):
+        a = np.asarray(frame)
+        assert a.ndim == 2 and a.strides[1] == a.itemsize
+        self._keep.append(a)
+        if a.dtype == np.float32:
+            rc = lib().d2pc_submit_f32(self._h, slot, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0])
+        elif a.dtype == np.uint8:
+            rc = lib().d2pc_submit_mono8(self._h, slot, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0])
+        else:
+            raise D2pcError(-2, "submit")
+        self._check(rc, "d2pc_submit")
+
+    def wait(self, slot: int) -> np.ndarray:
+        cl = Cloud()
+        self._check(lib().d2pc_wait(self._h, slot, C.byref(cl)), "d2pc_wait")
+        self.last_cloud = cl
+        return cl.bytes_view().copy()
+
+    def process_stream(self, frames: np.ndarray, collect: bool = True, sink=None, n_frames: int | None = None):
+        """frames: (F,H,W) u8 or f32 (numpy or PinnedArray.array).  n_frames > F cycles through the array
+        as a ring.  Returns the list of clouds if collect."""
+        assert frames.ndim == 3 and frames.strides[2] == frames.itemsize
+        out = []
+
+        def _sink(user, idx, cloud):
+            if sink is not None:
+                sink(idx, cloud.contents)
+            if collect:
+                out.append(cloud.contents.bytes_view().copy())
+
+        cb = CLOUD_SINK(_sink) if (collect or sink is not None) else C.cast(None, CLOUD_SINK)
+        f, h, w = frames.shape
+        rc = lib().d2pc_process_stream(self._h, frames.ctypes.data, n_frames or f, frames.strides[0], f,
+                                       1 if frames.dtype == np.float32 else 0, w, h, frames.strides[1], cb, None)
+        self._check(rc, "d2pc_process_stream")
+        return out
+
+    # -- device entry points (pointers are raw CUDA device addresses, e.g. torch.Tensor.data_ptr())
+    def reproject_f32_device(self, d_disp, n_frames, w, h, step, frame_stride, d_points, points_stride, d_counts=0):
+        self._check(lib().d2pc_reproject_f32_device(self._h, d_disp, n_frames, w, h, step, frame_stride, d_points,
+                                                    points_stride, d_counts or None), "d2pc_reproject_f32_device")
+
+    def reproject_mono8_device(self, d_img, n_frames, w, h, step, frame_stride, d_points, points_stride, d_counts=0):
+        self._check(lib().d2pc_reproject_mono8_device(self._h, d_img, n_frames, w, h, step, frame_stride, d_points,
+                                                      points_stride, d_counts or None), "d2pc_reproject_mono8_device")
+
+    def median_u8_device(self, d_src, w, h, src_step, d_dst, dst_step, ksize):
+        self._check(lib().d2pc_median_u8_device(self._h, d_src, w, h, src_step, d_dst, dst_step, ksize),
+                    "d2pc_median_u8_device")
+
+    def compute_stream(self) -> int:
+        return int(lib().d2pc_compute_stream(self._h) or 0)
+
+    def sync(self):
+        self._check(lib().d2pc_sync(self._h), "d2pc_sync")
+
+    def launch_count(self) -> int:
+        return int(lib().d2pc_launch_count(self._h))
+
+    # -- fusion
+    def fuse_geometry(self, w, h):
+        r1, r2, rc_, dims = (np.zeros(4, np.int32), np.zeros(4, np.int32), np.zeros(4, np.int32), np.zeros(3, np.int32))
+        st = lib().d2pc_fuse_geometry(self._h, w, h, *(a.ctypes.data_as(_i32p) for a in (r1, r2, rc_, dims)))
+        return st, tuple(map(int, r1)), tuple(map(int, r2)), tuple(map(int, rc_)), tuple(map(int, dims))
+
+    def fuse(self, d1, d2, s1, s2):
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (d1, d2, s1, s2)]
+        h, w = arrs[0].shape
+        fused, combined = Image(), Image()
+        self._check(lib().d2pc_fuse(self._h, *(a.ctypes.data for a in arrs), w, h, w, C.byref(fused),
+                                    C.byref(combined)), "d2pc_fuse")
+        return fused.array().copy(), combined.array().copy()
+
+    def fuse_device(self, d_d1, d_d2, d_s1, d_s2, w, h, step, d_fused, d_combined=0):
+        self._check(lib().d2pc_fuse_device(self._h, d_d1, d_d2, d_s1, d_s2, w, h, step, d_fused, d_combined or None),
+                    "d2pc_fuse_device")
+
+    def fuse_then_process(self, d1, d2, s1, s2) -> np.ndarray:
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (d1, d2, s1, s2)]
+        h, w = arrs[0].shape
+        cl = Cloud()
+        self._check(lib().d2pc_fuse_then_process(self._h, *(a.ctypes.data for a in arrs), w, h, w, C.byref(cl)),
+                    "d2pc_fuse_then_process")
+        self.last_cloud = cl
+        return cl.bytes_view().copy()
+
+    def serialize_pointcloud2(self, cloud: Cloud, seq=0, sec=0, nsec=0) -> bytes:
+        need = lib().d2pc_serialize_pointcloud2(self._h, C.byref(cloud), seq, sec, nsec, None, 0)
+        buf = (C.c_uint8 * need)()
+        lib().d2pc_serialize_pointcloud2(self._h, C.byref(cloud), seq, sec, nsec, buf, need)
+        return bytes(buf)
+
+
+def device_count() -> int:
+    return int(lib().d2pc_device_count())

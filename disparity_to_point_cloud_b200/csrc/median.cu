@@ -1,0 +1,205 @@
+// median.cu -- exact KxK median of CV_8UC1 images on sm_100a, replicate border.
+//
+// Replaces cv::medianBlur(img, out, 11)  src/disparity_to_point_cloud.cpp:55-57
+//      and cv::medianBlur(img, img, 3)   src/depth_map_fusion.cpp:124
+// (the result is an order statistic of 8-bit data, so any exact algorithm is
+// bit-identical to OpenCV's; SURVEY.md A.4 pins the border as replicate).
+//
+// Algorithm: sliding-histogram (Huang) median, one output column per thread,
+// sliding DOWN a strip of rows.  Each warp owns 32 adjacent columns and keeps
+//   * a 256-bin x 32-lane histogram of 8-bit counters in shared memory, laid
+//     out so that lane L only ever touches bank L (conflict-free for any data),
+//   * a ring of the K most recent input rows (32+K-1 bytes each).
+// Moving one row down removes K pixels and adds K pixels per thread, then the
+// running median walks a few bins.  Cost is O(K) per output, independent of
+// how disordered the image is (uniform noise is not a worst case).
+#include "median.h"
+
+#include <cstdint>
+
+namespace d2pc {
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kRingPitch = 48;  // >= 32 + 15 - 1, multiple of 4
+
+struct MedianArgs {
+  const uint8_t *src;
+  uint8_t *dst;
+  size_t src_step, dst_step, src_frame_stride, dst_frame_stride;
+  int width, height;
+  int ox0, oy0, ow, oh;  // output region (inside the image); dst is addressed with image coordinates
+  int strip_rows, n_colblk, n_strip;
+  uint32_t units_per_frame, total_units;
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// byte address of counter (bin, lane) inside a warp's 8 KB histogram
+__device__ __forceinline__ uint32_t hist_addr(uint32_t bin, uint32_t lane) {
+  return (((bin >> 2) * 32u + lane) << 2) | (bin & 3u);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_constant__ MedianArgs a) {
+  constexpr int R = K / 2;
+  constexpr int kRank = (K * K) / 2;
+  __shared__ __align__(16) uint8_t s_hist[kWarps][256 * 32];
+  __shared__ __align__(4) uint8_t s_ring[kWarps][K][kRingPitch];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  uint8_t *hist = s_hist[wic];
+  uint8_t(*ring)[kRingPitch] = s_ring[wic];
+
+  for (uint32_t unit = blockIdx.x * kWarps + wic; unit < a.total_units; unit += gridDim.x * kWarps) {
+    const uint32_t f = unit / a.units_per_frame;
+    const uint32_t rem = unit - f * a.units_per_frame;
+    const int strip = rem / a.n_colblk;
+    const int cb = rem - strip * a.n_colblk;
+    const int x0 = a.ox0 + cb * 32;
+    const int y_first = a.oy0 + strip * a.strip_rows;
+    const int y_end = min(y_first + a.strip_rows, a.oy0 + a.oh);
+    const uint8_t *src = a.src + (size_t)f * a.src_frame_stride;
+    uint8_t *dst = a.dst + (size_t)f * a.dst_frame_stride;
+    const bool col_ok = (x0 + lane) < (a.ox0 + a.ow);
+
+    // columns this lane fetches for every ring row (replicate border = clamp)
+    const int gx_a = clampi(x0 - R + lane, 0, a.width - 1);
+    const int gx_b = clampi(x0 - R + 32 + lane, 0, a.width - 1);
+
+    // ---- zero the histogram (warp-cooperative, 16 B per store)
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < (256 * 32) / (32 * 16); ++i)
+      reinterpret_cast<uint4 *>(hist)[i * 32 + lane] = make_uint4(0, 0, 0, 0);
+
+    // ---- fill the ring with window rows of the first output row
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const uint8_t *row = src + (size_t)clampi(y_first - R + s, 0, a.height - 1) * a.src_step;
+      ring[s][lane] = row[gx_a];
+      if (lane < K - 1) ring[s][32 + lane] = row[gx_b];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int s = 0; s < K; ++s) {
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const uint32_t ad = hist_addr(ring[s][lane + dx], lane);
+        hist[ad] = hist[ad] + 1;
+      }
+    }
+    // ---- initial median: walk 4 bins (one word) at a time, then bin by bin
+    int med = 0, below = 0;
+    {
+      int w = 0;
+      for (; w < 64; ++w) {
+        const uint32_t word = reinterpret_cast<const uint32_t *>(hist)[w * 32 + lane];
+        const int s4 = (word & 0xff) + ((word >> 8) & 0xff) + ((word >> 16) & 0xff) + (word >> 24);
+        if (below + s4 > kRank) break;
+        below += s4;
+      }
+      med = w * 4;
+      while (below + (int)hist[hist_addr(med, lane)] <= kRank) {
+        below += hist[hist_addr(med, lane)];
+        ++med;
+      }
+    }
+
+    int slot = 0;  // ring slot holding the oldest window row
+    for (int y = y_first; y < y_end; ++y) {
+      if (col_ok) dst[(size_t)y * a.dst_step + x0 + lane] = (uint8_t)med;
+      if (y + 1 >= y_end) break;
+      // prefetch the row entering the window
+      const uint8_t *row = src + (size_t)clampi(y + 1 + R, 0, a.height - 1) * a.src_step;
+      const uint8_t na = row[gx_a];
+      const uint8_t nb = (lane < K - 1) ? row[gx_b] : (uint8_t)0;
+      // remove the oldest row
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const uint32_t v = ring[slot][lane + dx];
+        const uint32_t ad = hist_addr(v, lane);
+        hist[ad] = hist[ad] - 1;
+        below -= ((int)v < med) ? 1 : 0;
+      }
+      __syncwarp();
+      ring[slot][lane] = na;
+      if (lane < K - 1) ring[slot][32 + lane] = nb;
+      __syncwarp();
+      // add the new row
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const uint32_t v = ring[slot][lane + dx];
+        const uint32_t ad = hist_addr(v, lane);
+        hist[ad] = hist[ad] + 1;
+        below += ((int)v < med) ? 1 : 0;
+      }
+      slot = (slot + 1 == K) ? 0 : slot + 1;
+      // re-centre: invariant below <= kRank < below + hist[med]
+      while (below > kRank) {
+        --med;
+        below -= hist[hist_addr(med, lane)];
+      }
+      for (;;) {
+        const int hm = hist[hist_addr(med, lane)];
+        if (below + hm > kRank) break;
+        below += hm;
+        ++med;
+      }
+    }
+  }
+}
+
+template <int K>
+cudaError_t launch_k(const MedianArgs &a, int grid, cudaStream_t s) {
+  median_hist_kernel<K><<<grid, kThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_median_u8(const MedianLaunch &L, cudaStream_t stream, int *launches) {
+  if (launches) *launches = 0;
+  if (L.ow <= 0 || L.oh <= 0 || L.n_frames == 0 || L.width <= 0 || L.height <= 0) return cudaSuccess;
+  if (L.ksize < 3 || L.ksize > 15 || (L.ksize & 1) == 0) return cudaErrorInvalidValue;
+  MedianArgs a{};
+  a.src = L.src;
+  a.dst = L.dst;
+  a.src_step = L.src_step;
+  a.dst_step = L.dst_step;
+  a.src_frame_stride = L.src_frame_stride;
+  a.dst_frame_stride = L.dst_frame_stride;
+  a.width = L.width;
+  a.height = L.height;
+  a.ox0 = L.ox0;
+  a.oy0 = L.oy0;
+  a.ow = L.ow;
+  a.oh = L.oh;
+  a.n_colblk = (L.ow + 31) / 32;
+  // strip height: long strips amortise the K*K start-up, short ones fill the chip with warps
+  int strip = 64;
+  const uint64_t want = (uint64_t)L.sm_count * 16;
+  while (strip > 8 && (uint64_t)a.n_colblk * ((L.oh + strip - 1) / strip) * L.n_frames < want) strip >>= 1;
+  if (L.strip_rows > 0) strip = L.strip_rows;
+  a.strip_rows = strip;
+  a.n_strip = (L.oh + strip - 1) / strip;
+  a.units_per_frame = (uint32_t)a.n_colblk * (uint32_t)a.n_strip;
+  const uint64_t total = (uint64_t)a.units_per_frame * L.n_frames;
+  if (total > 0xffffffffull) return cudaErrorInvalidValue;
+  a.total_units = (uint32_t)total;
+  const uint64_t ctas = (total + kWarps - 1) / kWarps;
+  const uint64_t cap = (uint64_t)L.sm_count * 6;
+  const int grid = (int)(ctas < cap ? ctas : cap);
+  if (launches) *launches = 1;
+  switch (L.ksize) {
+    case 3: return launch_k<3>(a, grid, stream);
+    case 5: return launch_k<5>(a, grid, stream);
+    case 7: return launch_k<7>(a, grid, stream);
+    case 9: return launch_k<9>(a, grid, stream);
+    case 11: return launch_k<11>(a, grid, stream);
+    case 13: return launch_k<13>(a, grid, stream);
+    default: return launch_k<15>(a, grid, stream);
+  }
+}
+
+}  // namespace d2pc

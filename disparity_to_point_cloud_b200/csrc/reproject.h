@@ -1,0 +1,41 @@
+// reproject.h -- host-side launcher interface of reproject.cu
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <cuda_runtime.h>
+
+namespace d2pc {
+
+struct QParams;
+
+struct ReprojectLaunch {
+  const void *in = nullptr;  // device: frames of float32 or mono8 rows
+  bool in_is_f32 = true;
+  size_t step = 0, frame_stride = 0;
+  uint32_t n_frames = 0, width = 0, height = 0;
+  int border = 40;
+  float scale = 0.125f;      // mono8 only (cpp:61)
+  uint8_t *out = nullptr;    // device: points, frame f at out + f*out_stride_bytes
+  size_t out_stride_bytes = 0;
+  uint32_t *counts = nullptr;  // device, per frame (CROP_FINITE)
+  const QParams *Q = nullptr;  // host copy; travels in the kernel parameter bank
+  bool arith_fast = false;
+  bool compact = false;        // CROP_FINITE
+  // compaction scratch (device): tile descriptors, ticket counter, launch epoch
+  void *scratch = nullptr;
+  uint32_t *ticket = nullptr;
+  uint32_t epoch = 1;
+  int sm_count = 148;
+  // tuning / test knobs (0 = automatic)
+  int rows_per_unit = 0;
+  int ctas_per_sm = 0;
+  bool force_scalar = false;   // exercise the unaligned load path
+  bool force_generic = false;  // exercise the generic-Q exact path on a rectified Q
+};
+
+void make_qparams(const double q[16], QParams *out);
+size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border);
+cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int *launches);
+
+}  // namespace d2pc

@@ -1,0 +1,268 @@
+/*
+ * d2pc_b200.h -- C ABI of libd2pc_b200.so: the B200 (sm_100a) implementation of
+ * the per-frame hot path of PX4/disparity_to_point_cloud.
+ *
+ * The reference has no plugin/operator API: its boundary is the ROS1 callback
+ *   void Disparity2PCloud::DisparityCb(const sensor_msgs::ImageConstPtr&)
+ *       include/disparity_to_point_cloud/disparity_to_point_cloud.hpp:108
+ *       src/disparity_to_point_cloud.cpp:46-92
+ * and, for the fusion node, the four callbacks of
+ *       include/disparity_to_point_cloud/depth_map_fusion.hpp:127-130
+ *       src/depth_map_fusion.cpp:46-136.
+ * Each entry point below names the reference lines it replaces.  Plain
+ * pointers and sizes only; no C++ or torch types; no exception crosses this
+ * boundary; every function returns a d2pc_status (0 = OK, negative = error).
+ *
+ * Threading (reference: one ros::spin() thread, src/disparity_to_point_cloud_node.cpp:50):
+ * a context is single-caller.  Different contexts are independent and may live
+ * on different GPUs / host threads.
+ *
+ * There is NO CPU fallback: every compute entry point fails with
+ * D2PC_ERR_NO_DEVICE / D2PC_ERR_CUDA if the GPU path is unavailable.
+ *
+ * (file:line citations are relative to the reference repository root.)
+ */
+#ifndef D2PC_B200_H_
+#define D2PC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D2PC_ABI_VERSION 1
+
+typedef enum d2pc_status {
+  D2PC_OK = 0,
+  D2PC_ERR_INVALID_ARG = -1,  /* NULL pointer, bad enum, bad slot ...              */
+  D2PC_ERR_BAD_ENCODING = -2, /* image encoding other than mono8 / 8UC1 / 32FC1     */
+  D2PC_ERR_BAD_DIMS = -3,     /* width/height/step inconsistent or over capacity    */
+  D2PC_ERR_CUDA = -4,         /* a CUDA runtime call failed (see d2pc_last_cuda_error) */
+  D2PC_ERR_NO_DEVICE = -5,    /* no usable sm_100 device                            */
+  D2PC_ERR_NOMEM = -6,        /* host or device allocation failed                   */
+  D2PC_ERR_GEOMETRY = -7,     /* fusion crop rectangle leaves the image (cv::Mat ROI would throw) */
+  D2PC_ERR_NOT_READY = -8,    /* wait on a slot with nothing submitted / caches empty */
+  D2PC_ERR_BUFFER_TOO_SMALL = -9
+} d2pc_status;
+
+/* src/disparity_to_point_cloud.cpp:69-76: the reference's only point filter is
+ * the fixed border crop (CROP).  CROP_FINITE is an extension: crop, then drop
+ * points with a non-finite x, y or z, order preserved (decoupled look-back
+ * stream compaction). */
+typedef enum d2pc_filter_mode { D2PC_FILTER_CROP = 0, D2PC_FILTER_CROP_FINITE = 1 } d2pc_filter_mode;
+
+/* EXACT reproduces cv::reprojectImageTo3D's float64 rounding sequence bit for
+ * bit (src/disparity_to_point_cloud.cpp:63-64).  FAST is float32 only
+ * (<= 1e-5 relative to depth, not bit-exact). */
+typedef enum d2pc_arith_mode { D2PC_ARITH_EXACT = 0, D2PC_ARITH_FAST = 1 } d2pc_arith_mode;
+
+/* src/depth_map_fusion.cpp:150-235: the rule getFusedDistance dispatches to.
+ * GRAD_FILTER is the one the reference is compiled with. */
+typedef enum d2pc_fuse_rule {
+  D2PC_FUSE_GRAD_FILTER = 0,
+  D2PC_FUSE_MAX_DIST = 1,
+  D2PC_FUSE_MAX_DIST_UNLESS_BLACK = 2,
+  D2PC_FUSE_BETTER_SCORE = 3,
+  D2PC_FUSE_ONLY_GOOD_1 = 4,
+  D2PC_FUSE_ONLY_GOOD_AVG = 5,
+  D2PC_FUSE_OVERLAP = 6,
+  D2PC_FUSE_BLACK_TO_WHITE = 7
+} d2pc_fuse_rule;
+
+/* Every constant the reference hard-codes or reads from ROS params, with the
+ * reference values as defaults (d2pc_config_default). */
+typedef struct d2pc_config {
+  uint32_t struct_size; /* sizeof(d2pc_config), for ABI growth */
+  /* Disparity2PCloud */
+  double fx, fy, cx, cy, baseline; /* hpp:66-71, 84-88: 714.24, 713.5, 376, 240, 0.09 */
+  int32_t rect_width, rect_height; /* hpp:101-103: 752 x 480, independent of the frame size */
+  int32_t border;                  /* cpp:70,72: 40 */
+  int32_t median_ksize;            /* cpp:57: 11 (odd, 1 disables) */
+  float disparity_scale;           /* cpp:61: 1/8 */
+  int32_t filter_mode;             /* d2pc_filter_mode */
+  int32_t arith_mode;              /* d2pc_arith_mode */
+  char frame_id[64];               /* cpp:89: "/camera_optical_frame" */
+  int32_t verbose;                 /* cpp:82: print "Cloud size: N" when non-zero */
+  /* DepthMapFusion */
+  int32_t offset_x, offset_y; /* depth_map_fusion.hpp:76-77, launch/depth_map_fusion.launch:8-9 */
+  int32_t fuse_rule;          /* d2pc_fuse_rule */
+  int32_t fuse_median_ksize;  /* depth_map_fusion.cpp:124: 3 */
+  int32_t fuse_crop_left, fuse_crop_right, fuse_crop_top, fuse_crop_bottom; /* :130: 0,40,30,10 */
+  /* capacity / pipeline */
+  int32_t max_width, max_height; /* largest frame the context will see (buffers are sized once) */
+  int32_t max_batch;             /* frames per batched call chunk */
+  int32_t n_slots;               /* async pipeline depth (>= 1, default 3) */
+} d2pc_config;
+
+typedef struct d2pc_ctx d2pc_ctx;
+
+/* sensor_msgs/PointField as pcl::toROSMsg<pcl::PointXYZ> fills it. */
+typedef struct d2pc_point_field {
+  char name[8];
+  uint32_t offset;
+  uint8_t datatype; /* 7 = FLOAT32 */
+  uint32_t count;
+} d2pc_point_field;
+
+/* The sensor_msgs/PointCloud2 payload DisparityCb publishes
+ * (src/disparity_to_point_cloud.cpp:79-90).  `data` is library-owned pinned
+ * host memory, valid until the next call that uses the same slot. */
+typedef struct d2pc_cloud {
+  const uint8_t *data; /* width * 16 bytes: {f32 x, f32 y, f32 z, f32 1.0} */
+  uint32_t height;     /* 1 */
+  uint32_t width;      /* number of points */
+  uint32_t point_step; /* 16 */
+  uint32_t row_step;   /* 16 * width */
+  uint8_t is_bigendian; /* 0 */
+  uint8_t is_dense;     /* 0 in CROP mode (cpp:81); 1 in CROP_FINITE */
+  uint32_t n_fields;    /* 3 */
+  d2pc_point_field fields[3];
+} d2pc_cloud;
+
+/* A mono8 sensor_msgs/Image payload (fusion outputs). Library-owned pinned memory. */
+typedef struct d2pc_image {
+  const uint8_t *data;
+  uint32_t width, height, step;
+} d2pc_image;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+
+void d2pc_config_default(d2pc_config *cfg);
+
+/* Replaces the Disparity2PCloud / DepthMapFusion constructors
+ * (disparity_to_point_cloud.hpp:75-106, depth_map_fusion.hpp:97-124) minus the
+ * ROS wiring: selects the device, creates streams, sizes pinned + device
+ * buffers and derives Q from the intrinsics in cfg. */
+int d2pc_create(const d2pc_config *cfg, int device, d2pc_ctx **out);
+void d2pc_destroy(d2pc_ctx *ctx);
+
+/* cv::stereoRectify(K,0,K,0,Size(rect_w,rect_h),I,(-b,0,0)) -> Q, row-major 4x4
+ * (disparity_to_point_cloud.hpp:90-104).  Host only. */
+int d2pc_q_from_intrinsics(double fx, double fy, double cx, double cy, double baseline, int rect_w, int rect_h,
+                           double q_out[16]);
+int d2pc_set_q(d2pc_ctx *ctx, const double q[16]);
+int d2pc_get_q(const d2pc_ctx *ctx, double q_out[16]);
+int d2pc_set_filter_mode(d2pc_ctx *ctx, int filter_mode);
+int d2pc_set_arith_mode(d2pc_ctx *ctx, int arith_mode);
+
+/* ---- the disparity callback, host buffers (the reference-facing calls) ------ */
+
+/* Whole DisparityCb (src/disparity_to_point_cloud.cpp:46-92) on one mono8
+ * frame in host memory: H2D, median 11, x(1/8), reproject with Q, crop 40,
+ * pack {x,y,z,1}, D2H.  Synchronous: `out` is complete on return. */
+int d2pc_process_mono8(d2pc_ctx *ctx, const uint8_t *data, uint32_t width, uint32_t height, uint32_t step,
+                       d2pc_cloud *out);
+
+/* DisparityCb entered after convertTo (cpp:63 onwards) on a float disparity
+ * frame in host memory; step in bytes. */
+int d2pc_process_f32(d2pc_ctx *ctx, const float *disp, uint32_t width, uint32_t height, uint32_t step,
+                     d2pc_cloud *out);
+
+/* Asynchronous variants on pipeline slot `slot` (0 <= slot < n_slots): H2D,
+ * kernels and D2H are enqueued on three streams chained by events, so slots
+ * overlap.  The input buffer may be reused once d2pc_wait(slot) returns (it is
+ * read by the DMA engine directly when it is pinned -- see d2pc_host_alloc --
+ * and staged through library pinned memory otherwise, in which case it may be
+ * reused as soon as submit returns). */
+int d2pc_submit_mono8(d2pc_ctx *ctx, int slot, const uint8_t *data, uint32_t width, uint32_t height, uint32_t step);
+int d2pc_submit_f32(d2pc_ctx *ctx, int slot, const float *disp, uint32_t width, uint32_t height, uint32_t step);
+int d2pc_wait(d2pc_ctx *ctx, int slot, d2pc_cloud *out);
+
+/* Pinned host memory for inputs the caller wants DMA'd without staging. */
+int d2pc_host_alloc(void **ptr, size_t bytes);
+int d2pc_host_free(void *ptr);
+
+/* Streams `n_frames` same-sized frames through the slot pipeline and hands every finished cloud to `sink` in
+ * frame order (sink may be NULL: the clouds are then produced and dropped).  Frame i is read from
+ * frames + (i % ring_len) * frame_stride bytes (ring_len 0 means n_frames, i.e. a plain array); is_f32 selects
+ * the float vs mono8 entry.  This is the loop a subscriber thread would run; it is what bench.py's end-to-end
+ * figure times. */
+typedef void (*d2pc_cloud_sink)(void *user, uint64_t frame_index, const d2pc_cloud *cloud);
+int d2pc_process_stream(d2pc_ctx *ctx, const void *frames, uint64_t n_frames, size_t frame_stride, uint64_t ring_len,
+                        int is_f32, uint32_t width, uint32_t height, uint32_t step, d2pc_cloud_sink sink,
+                        void *user);
+
+/* ---- device-resident entry points (kernel-only figures, chaining) ---------- */
+
+/* All pointers are DEVICE pointers on the context's device; work is enqueued
+ * on the context's compute stream and NOT synchronised (d2pc_sync, or CUDA
+ * events recorded on d2pc_compute_stream()). */
+
+/* cpp:63-85 for a batch of float frames: frame f at d_disp + f*frame_stride
+ * bytes, rows `step` bytes apart.  Points of frame f start at
+ * d_points + f*points_stride bytes.  In CROP mode every frame produces
+ * (w-2b)*(h-2b) points; in CROP_FINITE mode d_counts[f] (uint32, may be NULL
+ * in CROP mode) receives the number of points kept. */
+int d2pc_reproject_f32_device(d2pc_ctx *ctx, const float *d_disp, uint32_t n_frames, uint32_t width,
+                              uint32_t height, size_t step, size_t frame_stride, uint8_t *d_points,
+                              size_t points_stride, uint32_t *d_counts);
+
+/* cpp:55-85 for a batch of mono8 frames (median ksize from the config). */
+int d2pc_reproject_mono8_device(d2pc_ctx *ctx, const uint8_t *d_img, uint32_t n_frames, uint32_t width,
+                                uint32_t height, size_t step, size_t frame_stride, uint8_t *d_points,
+                                size_t points_stride, uint32_t *d_counts);
+
+/* cv::medianBlur on CV_8UC1, replicate border (cpp:55-57 with ksize 11,
+ * depth_map_fusion.cpp:124 with ksize 3).  ksize odd, 3..15. */
+int d2pc_median_u8_device(d2pc_ctx *ctx, const uint8_t *d_src, uint32_t width, uint32_t height, size_t src_step,
+                          uint8_t *d_dst, size_t dst_step, int ksize);
+
+void *d2pc_compute_stream(d2pc_ctx *ctx); /* cudaStream_t */
+int d2pc_sync(d2pc_ctx *ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t d2pc_launch_count(const d2pc_ctx *ctx);
+
+/* ---- depth_map_fusion -------------------------------------------------------- */
+
+/* Geometry of src/depth_map_fusion.cpp:237-265 for a w x h frame: rect1 (map /
+ * score 1), rect2 (map / score 2, in the rotated frame), rectc (output
+ * container), each {x, y, w, h}; dims = {n, fused_w, fused_h}. */
+int d2pc_fuse_geometry(const d2pc_ctx *ctx, uint32_t width, uint32_t height, int rect1[4], int rect2[4],
+                       int rectc[4], int dims[3]);
+
+/* One DisparityCb1 + DisparityCb2 + publishFusedDepthMap pass
+ * (src/depth_map_fusion.cpp:46-62, 103-136) on four same-sized mono8 frames in
+ * host memory: rotate map/score 2, crop all four to the common square, merge
+ * per pixel, median 3, final border trim.  s1/s2 are the preprocessed score
+ * images (what the caches cropped_score_{1,2}_ hold, :77/:96).
+ * fused  -> what is published on /fused_depth_map (:134-136)
+ * combined -> what is published on /combined_score (:126-127); may be NULL. */
+int d2pc_fuse(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1, const uint8_t *s2,
+              uint32_t width, uint32_t height, uint32_t step, d2pc_image *fused, d2pc_image *combined);
+
+/* Same, device pointers, enqueued on the compute stream.  d_fused is
+ * fused_w x fused_h dense; d_combined n x n dense (may be NULL). */
+int d2pc_fuse_device(d2pc_ctx *ctx, const uint8_t *d_d1, const uint8_t *d_d2, const uint8_t *d_s1,
+                     const uint8_t *d_s2, uint32_t width, uint32_t height, size_t step, uint8_t *d_fused,
+                     uint8_t *d_combined);
+
+/* BASELINE config 5: fuse four host frames, then run the whole DisparityCb on
+ * the fused map without leaving the device. */
+int d2pc_fuse_then_process(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
+                           const uint8_t *s2, uint32_t width, uint32_t height, uint32_t step, d2pc_cloud *out);
+
+/* ---- ROS1 wire helpers (what Publisher::publish serialises) ------------------- */
+
+/* sensor_msgs/PointCloud2 with header {seq, stamp, cfg.frame_id}; returns the
+ * byte count (write happens only if cap suffices; pass NULL/0 to size). */
+size_t d2pc_serialize_pointcloud2(const d2pc_ctx *ctx, const d2pc_cloud *cloud, uint32_t seq, uint32_t stamp_sec,
+                                  uint32_t stamp_nsec, uint8_t *out, size_t cap);
+
+/* ---- diagnostics ---------------------------------------------------------------- */
+
+/* Tuning / test hook: integer knobs by name ("rows_per_unit", "ctas_per_sm", "median_strip", "force_scalar",
+ * "force_generic", "median_ksize", "border", "offset_x", "offset_y", "fuse_rule").  Not needed in normal use. */
+int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value);
+
+const char *d2pc_strerror(int status);
+const char *d2pc_last_cuda_error(const d2pc_ctx *ctx);
+int d2pc_abi_version(void);
+/* Devices with compute capability 10.x visible to the process. */
+int d2pc_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2PC_B200_H_ */

@@ -1,0 +1,157 @@
+"""GPU parity: the whole DisparityCb on mono8 frames (median 11 -> x1/8 -> reproject -> crop -> pack),
+the median kernel on its own, the slot pipeline and the wire serialisation."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_same_bits, golden
+from disparity_to_point_cloud_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import disparity_to_point_cloud_b200 as d2pc
+    with d2pc.Context() as c:
+        yield c
+
+
+@pytest.fixture(scope="module")
+def q():
+    return golden("q_golden.npz")["q"][0]
+
+
+def test_callback_golden_fixtures(ctx):
+    g = golden("callback_golden.npz")
+    ctx.set_q(g["q"])
+    for i in range(3):
+        assert_same_bits(ctx.process_mono8(g[f"img{i}"]), g[f"cloud{i}"], f"cv2 fixture #{i}")
+
+
+@pytest.mark.parametrize("w,h,kind", [(752, 480, "s2"), (640, 480, "s1"), (1280, 720, "s2"), (665, 665, "s1"),
+                                      (81, 81, "s1"), (131, 203, "s2"), (80, 80, "s1")])
+def test_mono8_callback_bit_exact(ctx, q, w, h, kind):
+    img = synth.s2_scene(h, w, 11) if kind == "s2" else synth.s1_uniform(h, w, 11)
+    assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, q), f"{w}x{h} {kind}")
+
+
+def test_mono8_strided_message(ctx, q):
+    """sensor_msgs/Image.step larger than width (A1: honour step)."""
+    buf = synth.s2_scene(300, 512, 12)
+    view = buf[:, 7:407]
+    assert_same_bits(ctx.process_mono8(view), oracle.disparity_cb_mono8(np.ascontiguousarray(view), q), "step")
+
+
+def test_mono8_4k(ctx, q):
+    img = synth.s2_scene(2160, 3840, 13)
+    assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, q), "4K mono8")
+
+
+@pytest.mark.parametrize("ksize", [3, 5, 11, 15])
+@pytest.mark.parametrize("w,h", [(96, 64), (7, 5), (333, 222), (32, 300), (1, 40), (40, 1)])
+def test_median_kernel_full_frame(ctx, ksize, w, h):
+    import torch
+    img = synth.s1_uniform(h, w, 14 + ksize)
+    d_src = torch.from_numpy(img).cuda()
+    d_dst = torch.zeros_like(d_src)
+    torch.cuda.synchronize()
+    ctx.median_u8_device(d_src.data_ptr(), w, h, w, d_dst.data_ptr(), w, ksize)
+    ctx.sync()
+    assert_same_bits(d_dst.cpu().numpy(), oracle.median_blur(img, ksize), f"median {ksize} {w}x{h}")
+
+
+def test_median_golden_cv2(ctx):
+    import torch
+    g = golden("median_golden.npz")
+    for i in range(4):
+        img = g[f"img{i}"]
+        h, w = img.shape
+        for k in (11, 3):
+            d_src = torch.from_numpy(img).cuda()
+            d_dst = torch.zeros_like(d_src)
+            torch.cuda.synchronize()
+            ctx.median_u8_device(d_src.data_ptr(), w, h, w, d_dst.data_ptr(), w, k)
+            ctx.sync()
+            assert_same_bits(d_dst.cpu().numpy(), g[f"m{k}_{i}"], f"cv2 median {k} #{i}")
+
+
+def test_median_smooth_and_constant(ctx):
+    import torch
+    for img in (np.full((100, 100), 255, np.uint8), np.zeros((64, 64), np.uint8),
+                np.tile(np.arange(200, dtype=np.uint8), (120, 1)), synth.s2_scene(480, 752, 15)):
+        h, w = img.shape
+        d_src = torch.from_numpy(np.ascontiguousarray(img)).cuda()
+        d_dst = torch.zeros_like(d_src)
+        torch.cuda.synchronize()
+        ctx.median_u8_device(d_src.data_ptr(), w, h, w, d_dst.data_ptr(), w, 11)
+        ctx.sync()
+        assert_same_bits(d_dst.cpu().numpy(), oracle.median_blur(np.ascontiguousarray(img), 11), "median")
+
+
+def test_mono8_device_batch(ctx, q):
+    import torch
+    f, h, w = 3, 240, 376
+    frames = np.stack([synth.s2_scene(h, w, 40 + i) for i in range(f)])
+    n = oracle.n_points(w, h)
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = torch.zeros((f, n * 16), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.reproject_mono8_device(d_in.data_ptr(), f, w, h, w, w * h, d_out.data_ptr(), n * 16)
+    ctx.sync()
+    got = d_out.cpu().numpy()
+    for i in range(f):
+        assert_same_bits(got[i], oracle.disparity_cb_mono8(frames[i], q), f"frame {i}")
+
+
+def test_slot_pipeline_and_stream(ctx, q):
+    """Config 2 shape: a 752x480 mono8 stream through the 3-slot H2D|kernel|D2H pipeline, order preserved."""
+    import disparity_to_point_cloud_b200 as d2pc
+    f, h, w = 12, 480, 752
+    pin = d2pc.PinnedArray((f, h, w), np.uint8)
+    for i in range(f):
+        pin.array[i] = synth.s2_scene(h, w, 50 + i)
+    clouds = ctx.process_stream(pin.array)
+    assert len(clouds) == f
+    for i in (0, 1, 5, 11):
+        assert_same_bits(clouds[i], oracle.disparity_cb_mono8(pin.array[i], q), f"stream frame {i}")
+    # explicit slots, pageable input, out-of-order wait
+    a, b = synth.s2_scene(h, w, 70), synth.s1_uniform(h, w, 71)
+    ctx.submit(0, a)
+    ctx.submit(1, b)
+    got_b = ctx.wait(1)
+    got_a = ctx.wait(0)
+    assert_same_bits(got_a, oracle.disparity_cb_mono8(a, q), "slot 0")
+    assert_same_bits(got_b, oracle.disparity_cb_mono8(b, q), "slot 1")
+    with pytest.raises(d2pc.D2pcError):
+        ctx.wait(2)  # nothing submitted
+    pin.free()
+
+
+def test_float_stream_matches_single_calls(ctx, q):
+    f, h, w = 7, 300, 420
+    frames = np.stack([synth.s4_stress(h, w, 80 + i) for i in range(f)])
+    clouds = ctx.process_stream(frames)
+    for i in range(f):
+        assert_same_bits(clouds[i], oracle.disparity_cb_f32(frames[i], q), f"frame {i}")
+
+
+def test_pointcloud2_wire_bytes(ctx, q):
+    img = synth.s2_scene(120, 136, 90)
+    ctx.process_mono8(img)
+    got = ctx.serialize_pointcloud2(ctx.last_cloud, seq=3, sec=1700000000, nsec=123456789)
+    want = oracle.serialize_pointcloud2(oracle.disparity_cb_mono8(img, q), seq=3, sec=1700000000, nsec=123456789)
+    assert got == want
+
+
+def test_bad_arguments(ctx):
+    import disparity_to_point_cloud_b200 as d2pc
+    import ctypes as C
+    cl = d2pc.Cloud()
+    L = d2pc.lib()
+    img = np.zeros((10, 10), np.uint8)
+    assert L.d2pc_process_mono8(ctx._h, None, 10, 10, 10, C.byref(cl)) == -1
+    assert L.d2pc_process_mono8(ctx._h, img.ctypes.data, 10, 10, 5, C.byref(cl)) == -3   # step < width
+    assert L.d2pc_process_mono8(ctx._h, img.ctypes.data, 0, 10, 10, C.byref(cl)) == -3
+    assert L.d2pc_submit_mono8(ctx._h, 99, img.ctypes.data, 10, 10, 10) == -1
+    assert L.d2pc_set_filter_mode(ctx._h, 7) == -1
