@@ -22,7 +22,6 @@
 #include "fusion.h"
 #include "median.h"
 #include "reproject.h"
-#include "reproject_math.cuh"
 
 using namespace d2pc;
 

@@ -28,7 +28,7 @@ namespace d2pc {
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kSegCols = 128;  // crop columns per warp-row: 32 lanes x 4
 
@@ -49,7 +49,8 @@ struct ReprojArgs {
   QParams Q;
 };
 
-enum { kMathRect = 0, kMathGeneric = 1, kMathFast = 2 };
+enum { kMathRect0 = 0, kMathRectW = 1, kMathGeneric = 2, kMathFast = 3 };
+#define D2PC_IS_RECT(m) ((m) == kMathRect0 || (m) == kMathRectW)
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
   float4 v;
@@ -88,103 +89,132 @@ __device__ __forceinline__ float load1<uint8_t>(const uint8_t *row, int col, flo
   return u8_to_disp(__ldcs(row + col), scale);
 }
 
+// Four pixels of one lane (columns u0, u0+32, u0+64, u0+96 of row v): the arithmetic is straight-line so the
+// four FP64 dependency chains interleave; the rare slow path is one warp-level branch afterwards.
 template <int kMath>
-__device__ __forceinline__ float4 point_of(const QParams &Q, double xd, double yd, bool neg0, int u, int v, float d) {
-  if constexpr (kMath == kMathRect) return reproject_exact_rectified(Q, xd, yd, neg0, u, v, d);
-  if constexpr (kMath == kMathGeneric) return reproject_exact_generic(Q.q, u, v, d);
-  return reproject_fast(Q.qf, u, v, d);
+__device__ __forceinline__ void points_of4(const QParams &Q, const double (&xd)[4], double yd, uint32_t xslow,
+                                           bool yslow, int u0, int v, const float (&d)[4], float4 (&p)[4]) {
+  if constexpr (D2PC_IS_RECT(kMath)) {
+    bool slow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      p[k] = reproject_exact_rectified<kMath == kMathRect0>(Q, xd[k], yd, yslow || ((xslow >> k) & 1u), d[k],
+                                                            slow[k]);
+    if (__builtin_expect(slow[0] || slow[1] || slow[2] || slow[3], 0)) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (slow[k]) p[k] = reproject_exact_slow(Q.q, u0 + 32 * k, v, d[k]);
+    }
+  } else if constexpr (kMath == kMathGeneric) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] = reproject_exact_generic(Q.q, u0 + 32 * k, v, d[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] = reproject_fast(Q.qf, u0 + 32 * k, v, d[k]);
+  }
+}
+
+template <int kMath>
+__device__ __forceinline__ float4 point_of(const QParams &Q, int u, int v, float d) {
+  if constexpr (D2PC_IS_RECT(kMath)) {
+    const double xd = rect_axis_const(u, Q.q03), yd = rect_axis_const(v, Q.q13);
+    bool slow;
+    float4 p = reproject_exact_rectified<kMath == kMathRect0>(
+        Q, xd, yd, rect_axis_slow(xd) || rect_axis_slow(yd) || Q.zd_slow, d, slow);
+    if (__builtin_expect(slow, 0)) p = reproject_exact_slow(Q.q, u, v, d);
+    return p;
+  } else if constexpr (kMath == kMathGeneric) {
+    return reproject_exact_generic(Q.q, u, v, d);
+  } else {
+    return reproject_fast(Q.qf, u, v, d);
+  }
 }
 
 // ---------------------------------------------------------------------------
 // CROP kernel
 // ---------------------------------------------------------------------------
-template <typename InT, bool kVec, int kMath>
-__global__ void __launch_bounds__(kThreads) reproject_crop_kernel(const __grid_constant__ ReprojArgs a) {
+template <typename InT, bool kVec, int kMath, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(const __grid_constant__ ReprojArgs a) {
   __shared__ __align__(16) float stage[kWarpsPerCta][2][kSegCols];
   const int lane = threadIdx.x & 31;
   const int wic = threadIdx.x >> 5;
   const QParams &Q = a.Q;
 
-  for (uint32_t unit = blockIdx.x * kWarpsPerCta + wic; unit < a.total_units; unit += gridDim.x * kWarpsPerCta) {
-    const uint32_t f = unit / a.units_per_frame;
-    const uint32_t rem = unit - f * a.units_per_frame;
-    const int rb = rem / a.n_seg;
-    const int seg = rem - rb * a.n_seg;
-    const int c_base = seg * kSegCols;
-    const int r_base = rb * a.rows_per_unit;
-    const int rows = min(a.rows_per_unit, a.ch - r_base);
+  // one work unit (128 crop columns x rows_per_unit crop rows) per warp; the hardware CTA scheduler balances
+  const uint32_t unit = blockIdx.x * kWarpsPerCta + wic;
+  if (unit >= a.total_units) return;
+  const uint32_t f = unit / a.units_per_frame;
+  const uint32_t rem = unit - f * a.units_per_frame;
+  const int rb = rem / a.n_seg;
+  const int seg = rem - rb * a.n_seg;
+  const int c_base = seg * kSegCols;
+  const int r_base = rb * a.rows_per_unit;
+  const int rows = min(a.rows_per_unit, a.ch - r_base);
 
-    // column constants (registers, whole unit) and row constants (one lane per row)
-    double xd[4];
-    uint32_t xneg0 = 0;
-    double yd_lane = 0.0;
-    if constexpr (kMath == kMathRect) {
+  // column constants live in registers for the whole unit; row constants are computed by one lane per row
+  double xd[4];
+  uint32_t xslow = 0;
+  double yd_lane = 0.0;
+  if constexpr (D2PC_IS_RECT(kMath)) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        xd[k] = rect_axis_const(a.border + c_base + 32 * k + lane, Q.q03);
-        xneg0 |= is_neg_zero(xd[k]) ? (1u << k) : 0u;
-      }
-      yd_lane = rect_axis_const(a.border + r_base + lane, Q.q13);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) xd[k] = 0.0;
+    for (int k = 0; k < 4; ++k) {
+      xd[k] = rect_axis_const(a.border + c_base + 32 * k + lane, Q.q03);
+      xslow |= rect_axis_slow(xd[k]) ? (1u << k) : 0u;
     }
+    if (Q.zd_slow) xslow = 0xfu;
+    yd_lane = rect_axis_const(a.border + r_base + lane, Q.q13);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xd[k] = 0.0;
+  }
 
-    const uint8_t *in_f = a.in + (size_t)f * a.frame_stride;
-    float4 *out_f = a.out + (size_t)f * a.out_frame_stride;
+  const uint8_t *in_row = a.in + (size_t)f * a.frame_stride + (size_t)(a.border + r_base) * a.step;
+  float4 *out_row = a.out + (size_t)f * a.out_frame_stride + (size_t)r_base * a.cw;
 
-    for (int r = 0; r < rows; r += 2) {
-      // ---- load two crop rows of this segment
-      float dd[2][4];
-      if constexpr (kVec) {
-        const int c4 = c_base + 4 * lane;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (r + j < rows && c4 < a.cw) {
-            const uint8_t *row = in_f + (size_t)(a.border + r_base + r + j) * a.step;
-            const float4 v = load4<InT>(row, a.border + c4, a.scale);
-            *reinterpret_cast<float4 *>(&stage[wic][j][4 * lane]) = v;
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dd[j][k] = stage[wic][j][32 * k + lane];
-        __syncwarp();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint8_t *row = in_f + (size_t)(a.border + r_base + r + j) * a.step;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = c_base + 32 * k + lane;
-            dd[j][k] = (r + j < rows && c < a.cw) ? load1<InT>(row, a.border + c, a.scale) : 0.0f;
-          }
-        }
-      }
-      // ---- compute + store
+  for (int r = 0; r < rows; r += 2, in_row += 2 * a.step, out_row += 2 * (size_t)a.cw) {
+    // ---- load two crop rows of this segment
+    float dd[2][4];
+    if constexpr (kVec) {
+      const int c4 = c_base + 4 * lane;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        if (r + j >= rows) break;
-        const int crow = r_base + r + j;
-        double yd = 0.0;
-        bool yneg0 = false;
-        if constexpr (kMath == kMathRect) {
-          yd = __shfl_sync(0xffffffffu, yd_lane, r + j);
-          yneg0 = is_neg_zero(yd) || Q.zd_neg0;
+        if (r + j < rows && c4 < a.cw) {
+          const float4 v = load4<InT>(in_row + (size_t)j * a.step, a.border + c4, a.scale);
+          *reinterpret_cast<float4 *>(&stage[wic][j][4 * lane]) = v;
         }
-        float4 *out_row = out_f + (size_t)crow * a.cw;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dd[j][k] = stage[wic][j][32 * k + lane];
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int c = c_base + 32 * k + lane;
-          if (c < a.cw) {
-            const float4 p = point_of<kMath>(Q, xd[k], yd, yneg0 || ((xneg0 >> k) & 1u), a.border + c, a.border + crow,
-                                             dd[j][k]);
-            st_stream_f4(out_row + c, p);
-          }
+          dd[j][k] = (r + j < rows && c < a.cw) ? load1<InT>(in_row + (size_t)j * a.step, a.border + c, a.scale) : 1.0f;
         }
       }
+    }
+    // ---- compute + store: lane L owns columns L, L+32, L+64, L+96 -> each store is a 512-byte burst
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (r + j >= rows) break;
+      double yd = 0.0;
+      bool yslow = false;
+      if constexpr (D2PC_IS_RECT(kMath)) {
+        yd = __shfl_sync(0xffffffffu, yd_lane, r + j);
+        yslow = rect_axis_slow(yd);
+      }
+      float4 p[4];
+      points_of4<kMath>(Q, xd, yd, xslow, yslow, a.border + c_base + lane, a.border + r_base + r + j, dd[j], p);
+      float4 *o = out_row + (size_t)j * a.cw + c_base + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c_base + 32 * k + lane < a.cw) st_stream_f4(o + 32 * k, p[k]);
     }
   }
 }
@@ -194,8 +224,10 @@ __global__ void __launch_bounds__(kThreads) reproject_crop_kernel(const __grid_c
 // ---------------------------------------------------------------------------
 // Tile = kTilePts consecutive crop pixels in row-major order of one frame.
 // Descriptor word: [63:34] launch epoch, [33:32] flag, [31:0] value.
+constexpr int kCWarps = 8;
+constexpr int kCThreads = kCWarps * 32;
 constexpr int kItems = 8;                      // pixels per thread
-constexpr int kTilePts = kThreads * kItems;    // 2048
+constexpr int kTilePts = kCThreads * kItems;   // 2048
 constexpr uint32_t kFlagAggregate = 1, kFlagPrefix = 2;
 
 __device__ __forceinline__ unsigned long long desc_pack(uint32_t epoch, uint32_t flag, uint32_t value) {
@@ -211,9 +243,9 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
 }
 
 template <typename InT, bool kVec, int kMath>
-__global__ void __launch_bounds__(kThreads) reproject_compact_kernel(const __grid_constant__ ReprojArgs a) {
+__global__ void __launch_bounds__(kCThreads) reproject_compact_kernel(const __grid_constant__ ReprojArgs a) {
   __shared__ __align__(16) float4 tile_pts[kTilePts];  // 32 KB: the compacted tile
-  __shared__ uint32_t warp_sums[kWarpsPerCta];
+  __shared__ uint32_t warp_sums[kCWarps];
   __shared__ uint32_t s_tile, s_excl;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const QParams &Q = a.Q;
@@ -267,12 +299,7 @@ __global__ void __launch_bounds__(kThreads) reproject_compact_kernel(const __gri
         const int crow = idx / (uint32_t)a.cw;
         const int c = idx - crow * a.cw;
         const int u = a.border + c, v = a.border + crow;
-        if constexpr (kMath == kMathRect) {
-          const double xd = rect_axis_const(u, Q.q03), yd = rect_axis_const(v, Q.q13);
-          pts[i] = reproject_exact_rectified(Q, xd, yd, is_neg_zero(xd) || is_neg_zero(yd) || Q.zd_neg0, u, v, dd[i]);
-        } else {
-          pts[i] = point_of<kMath>(Q, 0.0, 0.0, false, u, v, dd[i]);
-        }
+        pts[i] = point_of<kMath>(Q, u, v, dd[i]);
         keep |= point_is_finite(pts[i]) ? (1u << i) : 0u;
       }
     }
@@ -288,7 +315,7 @@ __global__ void __launch_bounds__(kThreads) reproject_compact_kernel(const __gri
     __syncthreads();
     uint32_t warp_off = 0, tile_total = 0;
 #pragma unroll
-    for (int w = 0; w < kWarpsPerCta; ++w) {
+    for (int w = 0; w < kCWarps; ++w) {
       const uint32_t s = warp_sums[w];
       if (w < wic) warp_off += s;
       tile_total += s;
@@ -338,21 +365,26 @@ __global__ void __launch_bounds__(kThreads) reproject_compact_kernel(const __gri
       if (keep & (1u << i)) tile_pts[local++] = pts[i];
     __syncthreads();
     float4 *out_f = a.out + (size_t)f * a.out_frame_stride + s_excl;
-    for (uint32_t i = threadIdx.x; i < tile_total; i += kThreads) st_stream_f4(out_f + i, tile_pts[i]);
+    for (uint32_t i = threadIdx.x; i < tile_total; i += kCThreads) st_stream_f4(out_f + i, tile_pts[i]);
   }
 }
 
 template <typename InT, int kMath>
-cudaError_t launch_typed(const ReprojArgs &a, bool vec, bool compact, int grid, cudaStream_t s) {
+cudaError_t launch_typed(const ReprojArgs &a, bool vec, bool compact, int grid, int min_blocks, cudaStream_t s) {
   if (compact) {
     if (vec && a.cw % 4 == 0)
-      reproject_compact_kernel<InT, true, kMath><<<grid, kThreads, 0, s>>>(a);
+      reproject_compact_kernel<InT, true, kMath><<<grid, kCThreads, 0, s>>>(a);
     else
-      reproject_compact_kernel<InT, false, kMath><<<grid, kThreads, 0, s>>>(a);
+      reproject_compact_kernel<InT, false, kMath><<<grid, kCThreads, 0, s>>>(a);
   } else if (vec) {
-    reproject_crop_kernel<InT, true, kMath><<<grid, kThreads, 0, s>>>(a);
+    switch (min_blocks) {  // 128-thread CTAs: 4 -> <=128 regs, 6 -> 80, 7 -> 72, 8 -> 64
+      case 4: reproject_crop_kernel<InT, true, kMath, 4><<<grid, kThreads, 0, s>>>(a); break;
+      case 6: reproject_crop_kernel<InT, true, kMath, 6><<<grid, kThreads, 0, s>>>(a); break;
+      case 8: reproject_crop_kernel<InT, true, kMath, 8><<<grid, kThreads, 0, s>>>(a); break;
+      default: reproject_crop_kernel<InT, true, kMath, 7><<<grid, kThreads, 0, s>>>(a); break;
+    }
   } else {
-    reproject_crop_kernel<InT, false, kMath><<<grid, kThreads, 0, s>>>(a);
+    reproject_crop_kernel<InT, false, kMath, 6><<<grid, kThreads, 0, s>>>(a);
   }
   return cudaGetLastError();
 }
@@ -387,7 +419,12 @@ void make_qparams(const double q[16], QParams *out) {
   volatile double z = 0.0;
   const double h2 = z + q[11];
   P.zd = (double)(float)h2;
-  P.zd_neg0 = (bits(P.zd) == 0x8000000000000000ull) ? 1 : 0;
+  const uint64_t zb = bits(P.zd);
+  P.zd_slow = ((zb << 1) == 0 || ((zb >> 52) & 0x7ff) == 0x7ff) ? 1 : 0;
+  {
+    uint32_t zi = (zb << 1) == 0 ? 0xFFC00000u : (uint32_t)(((zb >> 63) << 31) | 0x7f800000u);
+    memcpy(&P.zinf, &zi, 4);
+  }
   *out = P;
 }
 
@@ -434,7 +471,8 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
                    (L.frame_stride % valign == 0) && ((size_t)L.border * esz % valign == 0) &&
                    (cw % 4 == 0 || L.border >= 3) && !L.force_scalar;
 
-  int math = L.arith_fast ? kMathFast : (a.Q.rectified && !L.force_generic ? kMathRect : kMathGeneric);
+  const int math = L.arith_fast ? kMathFast
+                   : (a.Q.rectified && !L.force_generic ? (a.Q.q33_zero ? kMathRect0 : kMathRectW) : kMathGeneric);
   const bool compact = L.compact;
 
   int grid;
@@ -451,8 +489,8 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
   } else {
     // rows per unit: large units amortise the per-unit constants, small ones spread a lone frame over the chip
     a.n_seg = (int)((cw + kSegCols - 1) / kSegCols);
-    int rb = L.rows_per_unit > 0 ? L.rows_per_unit : 16;
-    const uint64_t want_units = (uint64_t)L.sm_count * kWarpsPerCta * 4;
+    int rb = L.rows_per_unit > 0 ? L.rows_per_unit : 8;
+    const uint64_t want_units = (uint64_t)L.sm_count * 32;
     while (rb > 2 && (uint64_t)a.n_seg * ((ch + rb - 1) / rb) * L.n_frames < want_units) rb >>= 1;
     if (rb > 32) rb = 32;
     rb &= ~1;
@@ -463,17 +501,17 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
     const uint64_t total = (uint64_t)a.units_per_frame * L.n_frames;
     if (total > 0xffffffffull) return cudaErrorInvalidValue;
     a.total_units = (uint32_t)total;
-    const uint64_t ctas = (total + kWarpsPerCta - 1) / kWarpsPerCta;
-    const uint64_t cap = (uint64_t)L.sm_count * (L.ctas_per_sm > 0 ? L.ctas_per_sm : 4);
-    grid = (int)(ctas < cap ? ctas : cap);
+    grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
   }
+  const int min_blocks = L.ctas_per_sm > 0 ? L.ctas_per_sm : 8;
   if (launches) *launches = 1;
 
 #define D2PC_DISPATCH(T)                                                          \
   switch (math) {                                                                 \
-    case kMathRect: return launch_typed<T, kMathRect>(a, vec, compact, grid, stream); \
-    case kMathGeneric: return launch_typed<T, kMathGeneric>(a, vec, compact, grid, stream); \
-    default: return launch_typed<T, kMathFast>(a, vec, compact, grid, stream);    \
+    case kMathRect0: return launch_typed<T, kMathRect0>(a, vec, compact, grid, min_blocks, stream); \
+    case kMathRectW: return launch_typed<T, kMathRectW>(a, vec, compact, grid, min_blocks, stream); \
+    case kMathGeneric: return launch_typed<T, kMathGeneric>(a, vec, compact, grid, min_blocks, stream); \
+    default: return launch_typed<T, kMathFast>(a, vec, compact, grid, min_blocks, stream);    \
   }
   if (L.in_is_f32) {
     D2PC_DISPATCH(float)

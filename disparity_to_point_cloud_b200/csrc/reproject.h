@@ -7,7 +7,18 @@
 
 namespace d2pc {
 
-struct QParams;
+// Q as the kernels consume it (travels in the kernel parameter bank).
+struct QParams {
+  double q[16];  // row-major 4x4, as given
+  // rectified-form constants (valid when rectified != 0)
+  double q03, q13, q32, q33;
+  double zd;     // (double)(float)((+0.0) + q23)
+  float qf[16];  // float32 copy of Q for FAST mode
+  float zinf;    // zd / (+0): +-inf, or the x86 NaN when zd == 0
+  int rectified;
+  int q33_zero;
+  int zd_slow;   // zd is +-0 / inf / NaN: the straight-line path must not be used
+};
 
 struct ReprojectLaunch {
   const void *in = nullptr;  // device: frames of float32 or mono8 rows

@@ -117,6 +117,7 @@ def test_generic_q_matrix(ctx):
         q3 = _default_q().copy()
         q3[0, 3] = -1e-300
         q3[1, 3] = -1e-300
+        ctx.set_q(q3)
         ctx.set_tuning("border", 0)
         d3 = synth.s3_float(40, 64, 5)
         assert_same_bits(ctx.process_f32(d3), oracle.crop_pack(oracle.reproject_image_to_3d(d3, q3), 0), "neg zero")
