@@ -22,6 +22,9 @@
 //   staged in shared memory -> coalesced 16-byte stores.
 #include "reproject.h"
 
+#include <algorithm>
+#include <cmath>
+
 #include "reproject_math.cuh"
 
 namespace d2pc {
@@ -46,6 +49,8 @@ struct ReprojArgs {
   unsigned long long *tile_desc;
   uint32_t *ticket;
   uint32_t epoch, tiles_per_frame;
+  const double *xtab, *ytab;  // (double)(float)(u + q03), (double)(float)(v + q13)
+  uint32_t d_sure_bits;       // float bits of the smallest |d| whose point is certainly finite (rect0 compaction)
   QParams Q;
 };
 
@@ -222,12 +227,25 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(co
 // ---------------------------------------------------------------------------
 // CROP_FINITE kernel: order-preserving stream compaction, decoupled look-back
 // ---------------------------------------------------------------------------
-// Tile = kTilePts consecutive crop pixels in row-major order of one frame.
-// Descriptor word: [63:34] launch epoch, [33:32] flag, [31:0] value.
+// A work unit is one crop row x 128 columns (one warp, 4 pixels per lane, same load + transpose as the CROP
+// kernel).  Units are numbered in row-major order, so consecutive units are a contiguous range of the frame's
+// point order.  A tile is kCIter x kCWarps = 32 consecutive units (<= 4096 pixels), one CTA per tile:
+//   warp   reprojects its 4 units (all loads issued up front), parks the points in its own shared-memory cells
+//          (SoA, conflict-free) and counts survivors with one __ballot_sync + popc per pixel slot;
+//   block  32 unit counts -> warp-shuffle scan -> unit offsets and the tile total (one barrier);
+//   grid   the tile total is published and the whole CTA runs the decoupled look-back (256 predecessors per
+//          step) over 64-bit {epoch, flag, value} descriptors to get the tile's exclusive prefix;
+//   warp   re-ballots its cells and stores survivors straight to their final place: every pixel slot is one
+//          contiguous run of 16-byte points.
+// Tiles never span frames; the look-back chain restarts at each frame.  Tile ids come from an atomic ticket, so
+// every predecessor of a tile has already started (forward progress does not depend on CTA dispatch order).
+// Descriptor: [63:34] launch epoch, [33:32] flag, [31:0] value.
 constexpr int kCWarps = 8;
 constexpr int kCThreads = kCWarps * 32;
-constexpr int kItems = 8;                      // pixels per thread
-constexpr int kTilePts = kCThreads * kItems;   // 2048
+constexpr int kCIter = 4;
+constexpr int kTileUnits = kCWarps * kCIter;      // 32
+constexpr int kTilePts = kTileUnits * kSegCols;   // 4096
+constexpr size_t kCompactSmem = (size_t)kTilePts * 12 + (size_t)kCWarps * kSegCols * 4;  // 52 KB
 constexpr uint32_t kFlagAggregate = 1, kFlagPrefix = 2;
 
 __device__ __forceinline__ unsigned long long desc_pack(uint32_t epoch, uint32_t flag, uint32_t value) {
@@ -242,140 +260,387 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// (double)(float)(i + q) for every image column / row, computed once per launch.  Entries the straight-line path
+// must not use (+-0, inf, NaN numerators: rect_axis_slow) are stored as NaN so consumers test one exponent field;
+// the slow path recomputes from Q and never reads the table.  xtab is padded by kSegCols entries.
+__global__ void rect_tables_kernel(double q03, double q13, int width, int height, double *xtab, double *ytab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  if (i < width + kSegCols) {
+    const double x = rect_axis_const(i, q03);
+    xtab[i] = rect_axis_slow(x) ? qnan : x;
+  }
+  if (i < height) {
+    const double y = rect_axis_const(i, q13);
+    ytab[i] = rect_axis_slow(y) ? qnan : y;
+  }
+}
+
 template <typename InT, bool kVec, int kMath>
-__global__ void __launch_bounds__(kCThreads) reproject_compact_kernel(const __grid_constant__ ReprojArgs a) {
-  __shared__ __align__(16) float4 tile_pts[kTilePts];  // 32 KB: the compacted tile
-  __shared__ uint32_t warp_sums[kCWarps];
-  __shared__ uint32_t s_tile, s_excl;
+__global__ void __launch_bounds__(kCThreads, 4) reproject_compact_kernel(const __grid_constant__ ReprojArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float *sx = reinterpret_cast<float *>(smem_raw);
+  float *sy = sx + kTilePts;
+  float *sz = sy + kTilePts;
+  float *stage = sz + kTilePts;  // [kCWarps][128]
+  __shared__ uint32_t unit_cnt[kTileUnits];
+  __shared__ uint32_t lb_sum[kCWarps], lb_hit[kCWarps];
+  __shared__ uint32_t s_tile;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const QParams &Q = a.Q;
-  const uint32_t pts_per_frame = (uint32_t)a.cw * (uint32_t)a.ch;
-  const uint32_t total_tiles = a.tiles_per_frame * (uint32_t)a.n_frames;
 
-  for (;;) {
-    // dynamic tile id: a tile's predecessors have all started, so the look-back cannot deadlock
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= total_tiles) break;
-    const uint32_t f = tile / a.tiles_per_frame;
-    const uint32_t t_in_f = tile - f * a.tiles_per_frame;
-    const uint8_t *in_f = a.in + (size_t)f * a.frame_stride;
+  if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t f = tile / a.tiles_per_frame;
+  const uint32_t t_in_f = tile - f * a.tiles_per_frame;
+  const uint8_t *in_f = a.in + (size_t)f * a.frame_stride;
 
-    // ---- load + reproject kItems pixels per thread (blocked: thread t owns pixels first .. first+kItems-1)
-    const uint32_t first = t_in_f * kTilePts + threadIdx.x * kItems;
-    float dd[kItems];
-    if constexpr (kVec) {  // cw % 4 == 0: a group of 4 never straddles a crop row
+  // ---- issue every load of this warp's kCIter units first
+  int crow[kCIter], c_base[kCIter];
+  bool unit_ok[kCIter];
+  float4 raw[kCIter];
+  float dds[kVec ? 1 : kCIter][4];
 #pragma unroll
-      for (int g = 0; g < kItems / 4; ++g) {
-        const uint32_t idx = first + 4 * g;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < pts_per_frame) {
-          const int crow = idx / (uint32_t)a.cw;
-          const int c = idx - crow * a.cw;
-          v = load4<InT>(in_f + (size_t)(a.border + crow) * a.step, a.border + c, a.scale);
-        }
-        dd[4 * g + 0] = v.x, dd[4 * g + 1] = v.y, dd[4 * g + 2] = v.z, dd[4 * g + 3] = v.w;
-      }
+  for (int m = 0; m < kCIter; ++m) {
+    const uint32_t unit = t_in_f * kTileUnits + m * kCWarps + wic;  // row-major (row, segment) index in the frame
+    unit_ok[m] = unit < a.units_per_frame;
+    crow[m] = unit_ok[m] ? (int)(unit / (uint32_t)a.n_seg) : 0;
+    c_base[m] = unit_ok[m] ? (int)(unit - (uint32_t)crow[m] * a.n_seg) * kSegCols : 0;
+    const uint8_t *in_row = in_f + (size_t)(a.border + crow[m]) * a.step;
+    if constexpr (kVec) {
+      const int c4 = c_base[m] + 4 * lane;
+      raw[m] = (unit_ok[m] && c4 < a.cw) ? load4<InT>(in_row, a.border + c4, a.scale) : make_float4(1.f, 1.f, 1.f, 1.f);
     } else {
 #pragma unroll
-      for (int i = 0; i < kItems; ++i) {
-        const uint32_t idx = first + i;
-        dd[i] = 0.f;
-        if (idx < pts_per_frame) {
-          const int crow = idx / (uint32_t)a.cw;
-          const int c = idx - crow * a.cw;
-          dd[i] = load1<InT>(in_f + (size_t)(a.border + crow) * a.step, a.border + c, a.scale);
-        }
+      for (int k = 0; k < 4; ++k) {
+        const int c = c_base[m] + 32 * k + lane;
+        dds[m][k] = (unit_ok[m] && c < a.cw) ? load1<InT>(in_row, a.border + c, a.scale) : 1.0f;
       }
     }
-    float4 pts[kItems];
-    uint32_t keep = 0;
-#pragma unroll
-    for (int i = 0; i < kItems; ++i) {
-      const uint32_t idx = first + i;
-      if (idx < pts_per_frame) {
-        const int crow = idx / (uint32_t)a.cw;
-        const int c = idx - crow * a.cw;
-        const int u = a.border + c, v = a.border + crow;
-        pts[i] = point_of<kMath>(Q, u, v, dd[i]);
-        keep |= point_is_finite(pts[i]) ? (1u << i) : 0u;
-      }
-    }
-    // ---- block-wide exclusive scan of per-thread counts
-    const uint32_t cnt = __popc(keep);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += n;
-    }
-    if (lane == 31) warp_sums[wic] = incl;
-    __syncthreads();
-    uint32_t warp_off = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < kCWarps; ++w) {
-      const uint32_t s = warp_sums[w];
-      if (w < wic) warp_off += s;
-      tile_total += s;
-    }
-    uint32_t local = warp_off + incl - cnt;
-
-    // ---- decoupled look-back (warp 0); tile 0 of a frame starts the chain
-    if (wic == 0) {
-      unsigned long long *desc = a.tile_desc + tile;
-      uint32_t excl = 0;
-      if (t_in_f == 0) {
-        if (lane == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, tile_total));
-      } else {
-        if (lane == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagAggregate, tile_total));
-        int look = (int)t_in_f - 1;  // predecessor window [look-31, look] within this frame
-        for (;;) {
-          const int my = look - lane;
-          unsigned long long dv = 0;
-          uint32_t flag = kFlagPrefix, val = 0;  // lanes before the frame start act as a zero prefix
-          if (my >= 0) {
-            do {
-              dv = ld_relaxed_u64(a.tile_desc + (tile - t_in_f) + my);
-            } while ((uint32_t)(dv >> 34) != a.epoch || ((dv >> 32) & 3u) == 0);
-            flag = (uint32_t)(dv >> 32) & 3u;
-            val = (uint32_t)dv;
-          }
-          const uint32_t pmask = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
-          // lanes nearer than (and including) the first PREFIX contribute
-          const int stop = pmask ? (__ffs(pmask) - 1) : 32;
-          uint32_t contrib = (lane <= stop) ? val : 0u;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-          excl += contrib;
-          if (pmask) break;
-          look -= 32;
-        }
-        if (lane == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, excl + tile_total));
-      }
-      if (lane == 0) {
-        s_excl = excl;
-        if (t_in_f == a.tiles_per_frame - 1 && a.counts) a.counts[f] = excl + tile_total;
-      }
-    }
-    // ---- compact into shared memory, then coalesced copy-out
-#pragma unroll
-    for (int i = 0; i < kItems; ++i)
-      if (keep & (1u << i)) tile_pts[local++] = pts[i];
-    __syncthreads();
-    float4 *out_f = a.out + (size_t)f * a.out_frame_stride + s_excl;
-    for (uint32_t i = threadIdx.x; i < tile_total; i += kCThreads) st_stream_f4(out_f + i, tile_pts[i]);
   }
+  // ---- reproject, park, count
+#pragma unroll
+  for (int m = 0; m < kCIter; ++m) {
+    float dd[4];
+    if constexpr (kVec) {
+      *reinterpret_cast<float4 *>(&stage[wic * kSegCols + 4 * lane]) = raw[m];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dd[k] = stage[wic * kSegCols + 32 * k + lane];
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dd[k] = dds[m][k];
+    }
+    const int v = a.border + crow[m], u0 = a.border + c_base[m] + lane;
+    double xd[4] = {0.0, 0.0, 0.0, 0.0}, yd = 0.0;
+    uint32_t xslow = 0;
+    bool yslow = false;
+    if constexpr (D2PC_IS_RECT(kMath)) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xd[k] = a.xtab[u0 + 32 * k];  // padded table; NaN marks numerators for the slow path
+        xslow |= (((uint32_t)__double2hiint(xd[k]) & 0x7ff00000u) == 0x7ff00000u) ? (1u << k) : 0u;
+      }
+      if (Q.zd_slow) xslow = 0xfu;
+      yd = a.ytab[v];
+      yslow = ((uint32_t)__double2hiint(yd) & 0x7ff00000u) == 0x7ff00000u;
+    }
+    float4 p[4];
+    points_of4<kMath>(Q, xd, yd, xslow, yslow, u0, v, dd, p);
+    uint32_t cnt = 0;
+    const int cell0 = (m * kCWarps + wic) * kSegCols + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool keep = unit_ok[m] && (c_base[m] + 32 * k + lane < a.cw) && point_is_finite(p[k]);
+      cnt += __popc(__ballot_sync(0xffffffffu, keep));
+      sx[cell0 + 32 * k] = keep ? p[k].x : __uint_as_float(0x7fc00000u);  // NaN marks a dropped cell
+      sy[cell0 + 32 * k] = p[k].y;
+      sz[cell0 + 32 * k] = p[k].z;
+    }
+    if (lane == 0) unit_cnt[m * kCWarps + wic] = cnt;
+  }
+  __syncthreads();
+  // ---- 32 unit counts -> exclusive offsets (every warp scans; it is five shuffles)
+  const uint32_t mine = lane < kTileUnits ? unit_cnt[lane] : 0u;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  const uint32_t tile_total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t excl_unit = incl - mine;
+
+  // ---- decoupled look-back, block-wide: 256 predecessors per step (thread j looks at tile t-1-j), so a chain
+  // through every concurrently running tile resolves in two or three steps.  The first tile of a frame starts
+  // the chain; predecessors before the frame start count as a zero prefix.
+  unsigned long long *desc = a.tile_desc + tile;
+  uint32_t excl = 0;
+  if (t_in_f == 0) {
+    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, tile_total));
+  } else {
+    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagAggregate, tile_total));
+    int look = (int)t_in_f - 1;
+    for (;;) {
+      const int my = look - (int)threadIdx.x;
+      uint32_t flag = kFlagPrefix, val = 0;
+      if (my >= 0) {
+        unsigned long long dv;
+        do {
+          dv = ld_relaxed_u64(a.tile_desc + (tile - t_in_f) + my);
+        } while ((uint32_t)(dv >> 34) != a.epoch || ((dv >> 32) & 3u) == 0);
+        flag = (uint32_t)(dv >> 32) & 3u;
+        val = (uint32_t)dv;
+      }
+      const uint32_t pmask = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
+      const int stop = pmask ? (__ffs(pmask) - 1) : 32;  // nearest predecessor in this warp's window with a prefix
+      uint32_t contrib = (lane <= stop) ? val : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+      if (lane == 0) lb_sum[wic] = contrib, lb_hit[wic] = pmask ? 1u : 0u;
+      __syncthreads();
+      bool done = false;
+#pragma unroll
+      for (int w = 0; w < kCWarps; ++w) {
+        if (!done) {
+          excl += lb_sum[w];
+          done = lb_hit[w] != 0u;
+        }
+      }
+      if (done) break;
+      look -= kCThreads;
+      __syncthreads();  // lb_* are rewritten next step
+    }
+    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, excl + tile_total));
+  }
+  if (threadIdx.x == 0 && t_in_f == a.tiles_per_frame - 1 && a.counts) a.counts[f] = excl + tile_total;
+  // ---- survivors go straight to their final place; each pixel slot is one contiguous run
+  float4 *out_f = a.out + (size_t)f * a.out_frame_stride + excl;
+#pragma unroll
+  for (int m = 0; m < kCIter; ++m) {
+    uint32_t pos = __shfl_sync(0xffffffffu, excl_unit, m * kCWarps + wic);
+    const int cell0 = (m * kCWarps + wic) * kSegCols + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x = sx[cell0 + 32 * k];
+      const bool keep = (x == x);
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) st_stream_f4(out_f + pos + __popc(bal & lt_mask), make_float4(x, sy[cell0 + 32 * k], sz[cell0 + 32 * k], 1.0f));
+      pos += __popc(bal);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CROP_FINITE, rectified Q with q33 == +-0 (the stereoRectify form): classify first, reproject after
+// ---------------------------------------------------------------------------
+// For this Q, whether a point is finite is decided by the disparity alone for all but a sliver of inputs:
+//   d == +-0, inf, NaN            -> W is +0 / NaN: the point is never finite              (dropped)
+//   |d| >= d_sure (normal float)  -> |n / (q32*d)| < 2^127 for every numerator in the frame (kept); d_sure is
+//                                    computed on the host from max |numerator| and |q32|
+//   anything else (denormal, or |d| < d_sure ~ 2^-117)  -> decided by the exact slow path  (rare)
+// So the tile is counted before any FP64 work, the look-back latency overlaps other CTAs, and the survivors are
+// reprojected straight into their final place: no parking of points, 4 KB of shared memory per CTA.
+template <typename InT, bool kVec, int kMinB>
+__global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_rect0_kernel(const __grid_constant__ ReprojArgs a) {
+  __shared__ __align__(16) float stage[kCWarps * kSegCols];
+  __shared__ uint32_t unit_cnt[kTileUnits];
+  __shared__ uint32_t lb_sum[kCWarps], lb_hit[kCWarps];
+  __shared__ uint32_t s_tile;
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const QParams &Q = a.Q;
+
+  if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t f = tile / a.tiles_per_frame;
+  const uint32_t t_in_f = tile - f * a.tiles_per_frame;
+  const uint8_t *in_f = a.in + (size_t)f * a.frame_stride;
+
+  // ---- this warp's kCIter units: (row, segment) of unit t*32 + 8m + w, stepping by 8 units (one division only)
+  int crow[kCIter], c_base[kCIter];
+  uint32_t cmask = 0;  // bit 4m+k: pixel slot k of unit m lies inside the crop
+  {
+    const uint32_t unit0 = t_in_f * kTileUnits + wic;
+    int row = (int)(unit0 / (uint32_t)a.n_seg), seg = (int)(unit0 - (uint32_t)row * a.n_seg);
+#pragma unroll
+    for (int m = 0; m < kCIter; ++m) {
+      const bool unit_ok = unit0 + m * kCWarps < a.units_per_frame;
+      crow[m] = unit_ok ? row : -1;
+      c_base[m] = unit_ok ? seg * kSegCols : 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cmask |= (unit_ok && c_base[m] + 32 * k + lane < a.cw) ? (1u << (4 * m + k)) : 0u;
+      seg += kCWarps;
+      while (seg >= a.n_seg) seg -= a.n_seg, ++row;
+    }
+  }
+  // ---- every load is issued first
+  float dd[kCIter][4];
+  {
+    float4 raw[kCIter];
+#pragma unroll
+    for (int m = 0; m < kCIter; ++m) {
+      const uint8_t *in_row = in_f + (size_t)(a.border + max(crow[m], 0)) * a.step;
+      if constexpr (kVec) {
+        const int c4 = c_base[m] + 4 * lane;
+        raw[m] = (crow[m] >= 0 && c4 < a.cw) ? load4<InT>(in_row, a.border + c4, a.scale) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          dd[m][k] = ((cmask >> (4 * m + k)) & 1u) ? load1<InT>(in_row, a.border + c_base[m] + 32 * k + lane, a.scale) : 0.0f;
+      }
+    }
+    if constexpr (kVec) {
+#pragma unroll
+      for (int m = 0; m < kCIter; ++m) {
+        *reinterpret_cast<float4 *>(&stage[wic * kSegCols + 4 * lane]) = raw[m];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dd[m][k] = stage[wic * kSegCols + 32 * k + lane];
+        __syncwarp();
+      }
+    }
+  }
+  // ---- classify (bit 4m+k of `keep`: this lane's pixel survives); the undecidable sliver is one rare branch
+  uint32_t keep = 0, sliver = 0;
+#pragma unroll
+  for (int m = 0; m < kCIter; ++m)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t mag = __float_as_uint(dd[m][k]) & 0x7fffffffu;
+      keep |= (mag - a.d_sure_bits < 0x7f800000u - a.d_sure_bits) ? (1u << (4 * m + k)) : 0u;  // d_sure <= |d| < inf
+      sliver |= (mag - 1u < a.d_sure_bits - 1u) ? (1u << (4 * m + k)) : 0u;                    // 0 < |d| < d_sure
+    }
+  keep &= cmask;
+  sliver &= cmask;
+  if (__builtin_expect(sliver != 0u, 0)) {
+#pragma unroll
+    for (int m = 0; m < kCIter; ++m)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if ((sliver >> (4 * m + k)) & 1u) {
+          const float4 p = reproject_exact_slow(Q.q, a.border + c_base[m] + 32 * k + lane, a.border + crow[m], dd[m][k]);
+          keep |= point_is_finite(p) ? (1u << (4 * m + k)) : 0u;
+        }
+  }
+#pragma unroll
+  for (int m = 0; m < kCIter; ++m) {
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt += __popc(__ballot_sync(0xffffffffu, (keep >> (4 * m + k)) & 1u));
+    if (lane == 0) unit_cnt[m * kCWarps + wic] = cnt;
+  }
+  __syncthreads();
+  const uint32_t mine = lane < kTileUnits ? unit_cnt[lane] : 0u;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  const uint32_t tile_total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t excl_unit = incl - mine;
+
+  // ---- decoupled look-back, block-wide (see reproject_compact_kernel)
+  unsigned long long *desc = a.tile_desc + tile;
+  uint32_t excl = 0;
+  if (t_in_f == 0) {
+    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, tile_total));
+  } else {
+    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagAggregate, tile_total));
+    int look = (int)t_in_f - 1;
+    for (;;) {
+      const int my = look - (int)threadIdx.x;
+      uint32_t flag = kFlagPrefix, val = 0;
+      if (my >= 0) {
+        unsigned long long dv;
+        do {
+          dv = ld_relaxed_u64(a.tile_desc + (tile - t_in_f) + my);
+        } while ((uint32_t)(dv >> 34) != a.epoch || ((dv >> 32) & 3u) == 0);
+        flag = (uint32_t)(dv >> 32) & 3u;
+        val = (uint32_t)dv;
+      }
+      const uint32_t pmask = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
+      const int stop = pmask ? (__ffs(pmask) - 1) : 32;
+      uint32_t contrib = (lane <= stop) ? val : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+      if (lane == 0) lb_sum[wic] = contrib, lb_hit[wic] = pmask ? 1u : 0u;
+      __syncthreads();
+      bool done = false;
+#pragma unroll
+      for (int w = 0; w < kCWarps; ++w) {
+        if (!done) {
+          excl += lb_sum[w];
+          done = lb_hit[w] != 0u;
+        }
+      }
+      if (done) break;
+      look -= kCThreads;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, excl + tile_total));
+  }
+  if (threadIdx.x == 0 && t_in_f == a.tiles_per_frame - 1 && a.counts) a.counts[f] = excl + tile_total;
+
+  // ---- reproject the survivors into their final place; each pixel slot is one contiguous run of points.
+  // The numerator tables hold NaN where the straight-line path must not be used (see rect_tables_kernel).
+  float4 *out_f = a.out + (size_t)f * a.out_frame_stride + excl;
+#pragma unroll
+  for (int m = 0; m < kCIter; ++m) {
+    uint32_t pos = __shfl_sync(0xffffffffu, excl_unit, m * kCWarps + wic);
+    if (crow[m] < 0) continue;  // warp-uniform
+    const int v = a.border + crow[m], u0 = a.border + c_base[m] + lane;
+    double xd[4];
+    uint32_t xslow = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xd[k] = a.xtab[u0 + 32 * k];  // the table is padded past the image width
+      xslow |= (((uint32_t)__double2hiint(xd[k]) & 0x7ff00000u) == 0x7ff00000u) ? (1u << k) : 0u;
+    }
+    const double yd = a.ytab[v];
+    const bool yslow = ((uint32_t)__double2hiint(yd) & 0x7ff00000u) == 0x7ff00000u;
+    float4 p[4];
+    points_of4<kMathRect0>(Q, xd, yd, xslow, yslow, u0, v, dd[m], p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool kp = (keep >> (4 * m + k)) & 1u;
+      const uint32_t bal = __ballot_sync(0xffffffffu, kp);
+      if (kp) st_stream_f4(out_f + pos + __popc(bal & lt_mask), p[k]);
+      pos += __popc(bal);
+    }
+  }
+}
+
+template <typename K>
+cudaError_t launch_compact(K kernel, const ReprojArgs &a, int grid, cudaStream_t s) {
+  // 52 KB of dynamic shared memory needs the opt-in on every instantiation (and on every device)
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCompactSmem);
+  if (e != cudaSuccess) return e;
+  kernel<<<grid, kCThreads, kCompactSmem, s>>>(a);
+  return cudaGetLastError();
 }
 
 template <typename InT, int kMath>
 cudaError_t launch_typed(const ReprojArgs &a, bool vec, bool compact, int grid, int min_blocks, cudaStream_t s) {
   if (compact) {
-    if (vec && a.cw % 4 == 0)
-      reproject_compact_kernel<InT, true, kMath><<<grid, kCThreads, 0, s>>>(a);
-    else
-      reproject_compact_kernel<InT, false, kMath><<<grid, kCThreads, 0, s>>>(a);
+    if constexpr (kMath == kMathRect0) {
+      if (a.d_sure_bits != 0) {  // classify-first kernel
+        if (!vec)
+          reproject_compact_rect0_kernel<InT, false, 3><<<grid, kCThreads, 0, s>>>(a);
+        else if (min_blocks == 3)
+          reproject_compact_rect0_kernel<InT, true, 3><<<grid, kCThreads, 0, s>>>(a);
+        else
+          reproject_compact_rect0_kernel<InT, true, 4><<<grid, kCThreads, 0, s>>>(a);
+        return cudaGetLastError();
+      }
+    }
+    return vec ? launch_compact(reproject_compact_kernel<InT, true, kMath>, a, grid, s)
+               : launch_compact(reproject_compact_kernel<InT, false, kMath>, a, grid, s);
   } else if (vec) {
     switch (min_blocks) {  // 128-thread CTAs: 4 -> <=128 regs, 6 -> 80, 7 -> 72, 8 -> 64
       case 4: reproject_crop_kernel<InT, true, kMath, 4><<<grid, kThreads, 0, s>>>(a); break;
@@ -428,13 +693,19 @@ void make_qparams(const double q[16], QParams *out) {
   *out = P;
 }
 
+static uint64_t compact_tiles_per_frame(long cw, long ch) {
+  const uint64_t n_seg = (uint64_t)((cw + kSegCols - 1) / kSegCols);
+  return (n_seg * (uint64_t)ch + kTileUnits - 1) / kTileUnits;
+}
+
+// tile descriptors (must start zeroed: epoch 0 means "never written")
 size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border) {
   const long cw = (long)width - 2L * border, ch = (long)height - 2L * border;
-  if (cw <= 0 || ch <= 0) return 256;
-  const uint64_t pts = (uint64_t)cw * ch;
-  const uint64_t tiles = (pts + kTilePts - 1) / kTilePts;
+  const uint64_t tiles = (cw > 0 && ch > 0) ? compact_tiles_per_frame(cw, ch) : 0;
   return (size_t)(tiles * n_frames * 8 + 256);
 }
+// per-column / per-row numerator tables of the rectified path
+size_t reproject_table_bytes(uint32_t width, uint32_t height) { return ((size_t)width + kSegCols + height) * 8 + 64; }
 
 cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int *launches) {
   const long cw = (long)L.width - 2L * L.border, ch = (long)L.height - 2L * L.border;
@@ -476,19 +747,46 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
   const bool compact = L.compact;
 
   int grid;
+  a.n_seg = (int)((cw + kSegCols - 1) / kSegCols);
   if (compact) {
-    const uint64_t pts = (uint64_t)cw * ch;
-    a.tiles_per_frame = (uint32_t)((pts + kTilePts - 1) / kTilePts);
+    a.units_per_frame = (uint32_t)a.n_seg * (uint32_t)ch;
+    a.tiles_per_frame = (uint32_t)compact_tiles_per_frame(cw, ch);
     a.tile_desc = static_cast<unsigned long long *>(L.scratch);
+    double *tabs = static_cast<double *>(L.tables);
+    a.xtab = tabs;
+    a.ytab = tabs + L.width + kSegCols;
     a.ticket = L.ticket;
     a.epoch = L.epoch;
     const uint64_t total = (uint64_t)a.tiles_per_frame * L.n_frames;
-    grid = (int)(total < (uint64_t)L.sm_count * 4 ? total : (uint64_t)L.sm_count * 4);
+    if (total > 0xffffffffull) return cudaErrorInvalidValue;
+    grid = (int)total;  // one CTA per tile; the ticket, not blockIdx, names the tile
     cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
+    if (math == kMathRect0 && !a.Q.zd_slow && !L.force_park) {
+      // |n| <= max_numer for every numerator of the frame; |q| = |n| / (|q32| * |d|) < 2^127 once
+      // |d| >= max_numer * 2^-127 / |q32|; doubled for margin, clamped to the smallest normal float.
+      const double aq32 = a.Q.q32 < 0 ? -a.Q.q32 : a.Q.q32;
+      auto mag = [](double x) { return x < 0 ? -x : x; };
+      double max_numer = mag(a.Q.zd);
+      max_numer = std::max(max_numer, mag(a.Q.q03) + (double)L.width + 1.0);
+      max_numer = std::max(max_numer, mag(a.Q.q13) + (double)L.height + 1.0);
+      double d_sure = 2.0 * max_numer * 0x1p-127 / aq32;
+      if (d_sure < 0x1p-126) d_sure = 0x1p-126;
+      if (d_sure < 3.0e38) {
+        float fs = (float)d_sure;
+        if ((double)fs < d_sure) fs = std::nextafter(fs, INFINITY);
+        memcpy(&a.d_sure_bits, &fs, 4);
+      }
+    }
+    if (a.Q.rectified && !L.arith_fast && !L.force_generic) {
+      const int n = (int)(L.width + kSegCols > L.height ? L.width + kSegCols : L.height);
+      rect_tables_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a.Q.q03, a.Q.q13, (int)L.width, (int)L.height, tabs,
+                                                            tabs + L.width + kSegCols);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      if (launches) *launches += 1;
+    }
   } else {
     // rows per unit: large units amortise the per-unit constants, small ones spread a lone frame over the chip
-    a.n_seg = (int)((cw + kSegCols - 1) / kSegCols);
     int rb = L.rows_per_unit > 0 ? L.rows_per_unit : 8;
     const uint64_t want_units = (uint64_t)L.sm_count * 32;
     while (rb > 2 && (uint64_t)a.n_seg * ((ch + rb - 1) / rb) * L.n_frames < want_units) rb >>= 1;
@@ -504,7 +802,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
     grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
   }
   const int min_blocks = L.ctas_per_sm > 0 ? L.ctas_per_sm : 8;
-  if (launches) *launches = 1;
+  if (launches) *launches += 1;
 
 #define D2PC_DISPATCH(T)                                                          \
   switch (math) {                                                                 \

@@ -35,6 +35,7 @@ struct ReprojectLaunch {
   bool compact = false;        // CROP_FINITE
   // compaction scratch (device): tile descriptors, ticket counter, launch epoch
   void *scratch = nullptr;
+  void *tables = nullptr;      // reproject_table_bytes(width, height)
   uint32_t *ticket = nullptr;
   uint32_t epoch = 1;
   int sm_count = 148;
@@ -43,10 +44,12 @@ struct ReprojectLaunch {
   int ctas_per_sm = 0;
   bool force_scalar = false;   // exercise the unaligned load path
   bool force_generic = false;  // exercise the generic-Q exact path on a rectified Q
+  bool force_park = false;     // CROP_FINITE: use the park-then-compact kernel even where classify-first applies
 };
 
 void make_qparams(const double q[16], QParams *out);
 size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border);
+size_t reproject_table_bytes(uint32_t width, uint32_t height);
 cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int *launches);
 
 }  // namespace d2pc

@@ -1,0 +1,318 @@
+// nodes.hpp -- C++ host mirror of the reference's two node classes, on top of the C ABI (d2pc_b200.h).
+//
+//   d2pc::Disparity2PCloud            include/disparity_to_point_cloud/disparity_to_point_cloud.hpp:60-109
+//   depth_map_fusion::DepthMapFusion  include/disparity_to_point_cloud/depth_map_fusion.hpp:63-155
+//
+// Same class names, callback names, topic names, queue sizes, latch flag, parameter names and defaults as the
+// reference; the bodies hand the pixels to libd2pc_b200.so instead of OpenCV / PCL.  Header-only and ROS-free:
+// the topic plumbing is the in-process `Bus` below (what roscpp's single-threaded spin does for one process),
+// so the classes run in the offline harness and in tests.  ros1_shim/ shows the same classes bound to a real
+// roscpp NodeHandle.
+//
+// Deliberate differences from the reference, all at the edges of the hot path:
+//   * cv_bridge::toCvCopy(msg, "mono8") converts colour encodings; here only mono8 / 8UC1 are accepted and
+//     anything else throws std::invalid_argument (the reference would throw cv_bridge::Exception for encodings
+//     it can not convert, src/disparity_to_point_cloud.cpp:50).
+//   * the nine printf progress lines per frame (cpp:47-91) are dropped; `verbose` prints "Cloud size: N".
+//   * MatchingScoreCb{1,2} cache the score image as received: the Gaussian/Sobel preprocessing chain
+//     (src/depth_map_fusion.cpp:70-76, 89-95) is outside this round's scope.
+//   * the six debug publishers of the fusion node (colourised views) are not produced.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <regex>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../d2pc_b200.h"
+#include "ros_lite.hpp"
+
+namespace d2pc_b200 {
+
+namespace sensor_msgs = ros_lite::sensor_msgs;
+
+// ---- a process-local stand-in for roscore + roscpp's NodeHandle ------------------------------------------
+class Bus {
+ public:
+  using ImageCb = std::function<void(const sensor_msgs::ImageConstPtr &)>;
+  using CloudCb = std::function<void(const sensor_msgs::PointCloud2 &)>;
+
+  // <remap from="/disparity" to="/throttled_depth_map"/>
+  void remap(const std::string &from, const std::string &to) { remaps_[from] = to; }
+  std::string resolve(const std::string &name) const {
+    auto it = remaps_.find(name);
+    return it == remaps_.end() ? name : it->second;
+  }
+  void set_param(const std::string &name, double v) { params_[name] = v; }
+  template <typename T>
+  bool get_param(const std::string &name, T &out) const {
+    auto it = params_.find(name);
+    if (it == params_.end()) return false;
+    out = static_cast<T>(it->second);
+    return true;
+  }
+  template <typename T>
+  void param(const std::string &name, T &out, T def) const {
+    if (!get_param(name, out)) out = def;
+  }
+
+  void subscribe_image(const std::string &topic, uint32_t queue_size, ImageCb cb) {
+    image_subs_[resolve(topic)].push_back({queue_size, std::move(cb)});
+  }
+  void subscribe_cloud(const std::string &topic, uint32_t queue_size, CloudCb cb) {
+    const std::string t = resolve(topic);
+    cloud_subs_[t].push_back({queue_size, cb});
+    auto it = latched_clouds_.find(t);  // a latched publisher re-delivers its last message to late subscribers
+    if (it != latched_clouds_.end()) cb(it->second);
+  }
+  struct Advertised {
+    std::string topic;
+    uint32_t queue_size;
+    bool latch;
+  };
+  std::string advertise(const std::string &topic, uint32_t queue_size, bool latch = false) {
+    const std::string t = resolve(topic);
+    advertised_.push_back({t, queue_size, latch});
+    return t;
+  }
+  void publish(const std::string &resolved_topic, const sensor_msgs::ImageConstPtr &msg) {
+    auto it = image_subs_.find(resolved_topic);
+    if (it != image_subs_.end())
+      for (auto &s : it->second) s.cb(msg);
+  }
+  void publish(const std::string &resolved_topic, const sensor_msgs::PointCloud2 &msg) {
+    for (const auto &a : advertised_)
+      if (a.topic == resolved_topic && a.latch) latched_clouds_[resolved_topic] = msg;
+    auto it = cloud_subs_.find(resolved_topic);
+    if (it != cloud_subs_.end())
+      for (auto &s : it->second) s.cb(msg);
+  }
+  const std::vector<Advertised> &advertised() const { return advertised_; }
+
+  // Reads <remap from= to=/> and <param name= value=/> out of a roslaunch file (launch/*.launch).
+  bool load_launch_file(const std::string &path) {
+    std::ifstream in(path);
+    if (!in) return false;
+    std::stringstream ss;
+    ss << in.rdbuf();
+    std::string xml = std::regex_replace(ss.str(), std::regex("<!--[\\s\\S]*?-->"), "");
+    auto attr = [](const std::string &tag, const std::string &name) {
+      std::smatch m;
+      return std::regex_search(tag, m, std::regex(name + "\\s*=\\s*\"([^\"]*)\"")) ? m[1].str() : std::string();
+    };
+    const std::regex tag_re("<(remap|param)\\b[^>]*>");
+    for (auto it = std::sregex_iterator(xml.begin(), xml.end(), tag_re); it != std::sregex_iterator(); ++it) {
+      const std::string tag = it->str();
+      if ((*it)[1] == "remap")
+        remap(attr(tag, "from"), attr(tag, "to"));
+      else
+        set_param(attr(tag, "name"), std::stod(attr(tag, "value")));
+    }
+    return true;
+  }
+
+ private:
+  template <typename Cb>
+  struct Sub {
+    uint32_t queue_size;
+    Cb cb;
+  };
+  std::map<std::string, std::string> remaps_;
+  std::map<std::string, double> params_;
+  std::map<std::string, std::vector<Sub<ImageCb>>> image_subs_;
+  std::map<std::string, std::vector<Sub<CloudCb>>> cloud_subs_;
+  std::map<std::string, sensor_msgs::PointCloud2> latched_clouds_;
+  std::vector<Advertised> advertised_;
+};
+
+inline void check(int status, const char *what, const d2pc_ctx *ctx = nullptr) {
+  if (status != D2PC_OK)
+    throw std::runtime_error(std::string(what) + ": " + d2pc_strerror(status) +
+                             (ctx ? std::string(" [") + d2pc_last_cuda_error(ctx) + "]" : std::string()));
+}
+
+// cv_bridge::toCvCopy(*msg, "mono8") for the encodings this library accepts.
+inline void require_mono8(const sensor_msgs::Image &msg) {
+  if (msg.encoding != "mono8" && msg.encoding != "8UC1")
+    throw std::invalid_argument("unsupported image encoding '" + msg.encoding + "' (mono8 / 8UC1 only)");
+  if (msg.step < msg.width || msg.data.size() < static_cast<size_t>(msg.step) * msg.height)
+    throw std::invalid_argument("sensor_msgs/Image: step / data size inconsistent");
+}
+
+}  // namespace d2pc_b200
+
+// ==========================================================================================================
+namespace d2pc {
+
+namespace sensor_msgs = ros_lite::sensor_msgs;
+
+class Disparity2PCloud {
+ private:
+  d2pc_b200::Bus &nh_;
+  std::string p_cloud_topic_;
+  // TODO (kept from the reference): import these with the calibration file or camera info topic
+  double fx_ = 714.24;
+  double fy_ = 713.5;
+  double cx_ = 376;
+  double cy_ = 240;
+  double base_line_ = 0.09;  // Omni-stereo
+  double Q_[16];
+  d2pc_ctx *ctx_ = nullptr;
+
+ public:
+  explicit Disparity2PCloud(d2pc_b200::Bus &nh, int device = 0, bool verbose = false) : nh_(nh) {
+    // hpp:77-81: subscribe "/disparity" queue 1; advertise "/point_cloud" queue 1 -- the reference passes `this`
+    // as the latch flag, so the publisher is latched.
+    nh_.subscribe_image("/disparity", 1, [this](const sensor_msgs::ImageConstPtr &m) { DisparityCb(m); });
+    p_cloud_topic_ = nh_.advertise("/point_cloud", 1, /*latch=*/true);
+    // hpp:84-88
+    nh_.param<double>("fx_", fx_, 714.24);
+    nh_.param<double>("fy_", fy_, 713.5);
+    nh_.param<double>("cx_", cx_, 376);
+    nh_.param<double>("cy_", cy_, 240);
+    nh_.param<double>("base_line_", base_line_, 0.09);
+    // hpp:90-104: Q from stereoRectify on a fixed 752x480 image size (done inside d2pc_create)
+    d2pc_config cfg;
+    d2pc_config_default(&cfg);
+    cfg.fx = fx_, cfg.fy = fy_, cfg.cx = cx_, cfg.cy = cy_, cfg.baseline = base_line_;
+    cfg.verbose = verbose ? 1 : 0;
+    d2pc_b200::check(d2pc_create(&cfg, device, &ctx_), "d2pc_create");
+    d2pc_get_q(ctx_, Q_);
+  }
+  ~Disparity2PCloud() { d2pc_destroy(ctx_); }
+  Disparity2PCloud(const Disparity2PCloud &) = delete;
+  Disparity2PCloud &operator=(const Disparity2PCloud &) = delete;
+
+  const double *Q() const { return Q_; }
+  d2pc_ctx *context() { return ctx_; }
+
+  // src/disparity_to_point_cloud.cpp:46-92
+  void DisparityCb(const sensor_msgs::ImageConstPtr &msg) {
+    d2pc_b200::require_mono8(*msg);
+    d2pc_cloud cloud;
+    d2pc_b200::check(d2pc_process_mono8(ctx_, msg->data.data(), msg->width, msg->height, msg->step, &cloud),
+                     "d2pc_process_mono8", ctx_);
+    sensor_msgs::PointCloud2 output;  // pcl::toROSMsg(*cloud, output), cpp:84-85
+    output.height = cloud.height;
+    output.width = cloud.width;
+    for (uint32_t i = 0; i < cloud.n_fields; ++i) {
+      sensor_msgs::PointField f;
+      f.name = cloud.fields[i].name;
+      f.offset = cloud.fields[i].offset;
+      f.datatype = cloud.fields[i].datatype;
+      f.count = cloud.fields[i].count;
+      output.fields.push_back(f);
+    }
+    output.is_bigendian = cloud.is_bigendian;
+    output.point_step = cloud.point_step;
+    output.row_step = cloud.row_step;
+    output.is_dense = cloud.is_dense;
+    output.data.assign(cloud.data, cloud.data + static_cast<size_t>(cloud.row_step) * cloud.height);
+    output.header.stamp = msg->header.stamp;             // cpp:87
+    output.header.frame_id = "/camera_optical_frame";    // cpp:89
+    nh_.publish(p_cloud_topic_, output);                 // cpp:90
+  }
+};
+
+}  // namespace d2pc
+
+// ==========================================================================================================
+namespace depth_map_fusion {
+
+namespace sensor_msgs = ros_lite::sensor_msgs;
+
+class DepthMapFusion {
+ private:
+  d2pc_b200::Bus &nh_;
+  std::string fused_topic_;
+  d2pc_ctx *ctx_ = nullptr;
+  // the reference caches cropped cv::Mat views (depth_map_fusion.hpp:79-85); the crop and the rotation are index
+  // arithmetic inside the fusion kernel, so the full frames are cached instead
+  sensor_msgs::Image depth_1_, depth_2_, score_1_, score_2_;
+  bool have_d1_ = false, have_d2_ = false, have_s1_ = false, have_s2_ = false;
+
+  void cache(const sensor_msgs::ImageConstPtr &msg, sensor_msgs::Image &slot, bool &have) {
+    d2pc_b200::require_mono8(*msg);
+    slot = *msg;
+    have = true;
+  }
+
+ public:
+  int offset_x_ = 0;
+  int offset_y_ = 0;
+  double scaling_factor_ = 1.0;
+
+  explicit DepthMapFusion(d2pc_b200::Bus &nh, int device = 0) : nh_(nh) {
+    // depth_map_fusion.hpp:97-104
+    nh_.subscribe_image("/disparity_1", 1, [this](const sensor_msgs::ImageConstPtr &m) { DisparityCb1(m); });
+    nh_.subscribe_image("/disparity_2", 1, [this](const sensor_msgs::ImageConstPtr &m) { DisparityCb2(m); });
+    nh_.subscribe_image("/matching_score_1", 1, [this](const sensor_msgs::ImageConstPtr &m) { MatchingScoreCb1(m); });
+    nh_.subscribe_image("/matching_score_2", 1, [this](const sensor_msgs::ImageConstPtr &m) { MatchingScoreCb2(m); });
+    // :106-117 (only the fused map is produced; the six debug views are visualisation)
+    fused_topic_ = nh_.advertise("/fused_depth_map", 5);
+    // :119-124
+    if (!nh_.get_param("offset_x", offset_x_)) std::fprintf(stderr, "[ WARN] Failed to load parameter offset_x\n");
+    if (!nh_.get_param("offset_y", offset_y_)) std::fprintf(stderr, "[ WARN] Failed to load parameter offset_y\n");
+    d2pc_config cfg;
+    d2pc_config_default(&cfg);
+    cfg.offset_x = offset_x_;
+    cfg.offset_y = offset_y_;
+    d2pc_b200::check(d2pc_create(&cfg, device, &ctx_), "d2pc_create");
+  }
+  ~DepthMapFusion() { d2pc_destroy(ctx_); }
+  DepthMapFusion(const DepthMapFusion &) = delete;
+  DepthMapFusion &operator=(const DepthMapFusion &) = delete;
+
+  void DisparityCb1(const sensor_msgs::ImageConstPtr &msg) { cache(msg, depth_1_, have_d1_); }  // cpp:46-52
+  void DisparityCb2(const sensor_msgs::ImageConstPtr &msg) {                                  // cpp:54-62
+    cache(msg, depth_2_, have_d2_);
+    publishFusedDepthMap(msg);
+  }
+  void MatchingScoreCb1(const sensor_msgs::ImageConstPtr &msg) { cache(msg, score_1_, have_s1_); }  // cpp:64-80
+  void MatchingScoreCb2(const sensor_msgs::ImageConstPtr &msg) { cache(msg, score_2_, have_s2_); }  // cpp:82-99
+
+  // src/depth_map_fusion.cpp:103-136
+  void publishFusedDepthMap(const sensor_msgs::ImageConstPtr &msg) {
+    if (!have_d1_ || !have_d2_ || !have_s1_ || !have_s2_) return;  // :108-111
+    const uint32_t w = depth_2_.width, h = depth_2_.height;
+    for (const sensor_msgs::Image *m : {&depth_1_, &score_1_, &score_2_})
+      if (m->width != w || m->height != h) throw std::invalid_argument("fusion inputs differ in size");
+    // d2pc_fuse wants one common step: repack any frame whose step differs
+    auto dense = [&](const sensor_msgs::Image &m, std::vector<uint8_t> &tmp) -> const uint8_t * {
+      if (m.step == w) return m.data.data();
+      tmp.resize(static_cast<size_t>(w) * h);
+      for (uint32_t y = 0; y < h; ++y) std::copy_n(m.data.data() + static_cast<size_t>(y) * m.step, w, tmp.data() + static_cast<size_t>(y) * w);
+      return tmp.data();
+    };
+    std::vector<uint8_t> t1, t2, t3, t4;
+    d2pc_image fused, combined;
+    d2pc_b200::check(d2pc_fuse(ctx_, dense(depth_1_, t1), dense(depth_2_, t2), dense(score_1_, t3),
+                               dense(score_2_, t4), w, h, w, &fused, &combined),
+                     "d2pc_fuse", ctx_);
+    // :113, :118-121: cropped_score_combined_ aliases cropped_score_1_, so after a fusion pass the cached score 1
+    // holds min(score1, score2) over the merged square until the next MatchingScoreCb1 replaces it.
+    int r1[4], r2[4], rc[4], dims[3];
+    d2pc_b200::check(d2pc_fuse_geometry(ctx_, w, h, r1, r2, rc, dims), "d2pc_fuse_geometry");
+    for (int i = 0; i < dims[0]; ++i)
+      std::copy_n(combined.data + static_cast<size_t>(i) * combined.step, dims[0],
+                  score_1_.data.data() + static_cast<size_t>(r1[1] + i) * score_1_.step + r1[0]);
+    auto out = std::make_shared<sensor_msgs::Image>();  // disparity->toImageMsg(fused_image), :134-135
+    out->header = msg->header;
+    out->height = fused.height;
+    out->width = fused.width;
+    out->encoding = "mono8";
+    out->is_bigendian = 0;
+    out->step = fused.width;
+    out->data.resize(static_cast<size_t>(fused.width) * fused.height);
+    for (uint32_t y = 0; y < fused.height; ++y)
+      std::copy_n(fused.data + static_cast<size_t>(y) * fused.step, fused.width, out->data.data() + static_cast<size_t>(y) * fused.width);
+    nh_.publish(fused_topic_, sensor_msgs::ImageConstPtr(out));  // :136
+  }
+};
+
+}  // namespace depth_map_fusion

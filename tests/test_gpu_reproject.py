@@ -193,17 +193,27 @@ def test_fast_mode_within_tolerance(ctx):
 
 
 # ---- CROP_FINITE (extension): order-preserving compaction ---------------------------------------
+@pytest.mark.parametrize("park", [0, 1])
 @pytest.mark.parametrize("w,h,kind", [(640, 480, "s2"), (1280, 720, "s2"), (333, 97, "s1"), (81, 81, "zeros"),
-                                      (400, 300, "nozeros"), (2000, 90, "s2")])
-def test_crop_finite_compaction(ctx, w, h, kind):
+                                      (400, 300, "nozeros"), (2000, 90, "s2"), (700, 300, "special")])
+def test_crop_finite_compaction(ctx, w, h, kind, park):
+    """park=0: classify-first kernel (rectified Q); park=1: park-then-compact kernel (any Q)."""
     import disparity_to_point_cloud_b200 as d2pc
     ctx.set_q(_default_q())
+    ctx.set_tuning("force_park", park)
     if kind == "s2":
         d = synth.s2_scene(h, w, 2).astype(np.float32) * np.float32(0.125)
     elif kind == "s1":
         d = synth.s3_float(h, w, 2)
     elif kind == "zeros":
         d = np.zeros((h, w), dtype=np.float32)
+    elif kind == "special":
+        # the sliver the classifier can not decide from d alone: denormals and |d| < ~2^-117, plus inf/NaN/-0
+        d = synth.s4_stress(h, w, 2)
+        flat = d.reshape(-1)
+        for i, v in enumerate([1e-45, 1e-40, 1.2e-38, 1e-37, 3e-36, 1e-35, 5e-34, -1e-37, -0.0, np.inf, -np.inf,
+                               np.nan, 3e38, -2.5]):
+            flat[i::29] = np.float32(v)
     else:
         d = np.full((h, w), 3.5, dtype=np.float32)
     want = oracle.filter_finite(oracle.disparity_cb_f32(d, _default_q()))
@@ -216,6 +226,24 @@ def test_crop_finite_compaction(ctx, w, h, kind):
         assert_same_bits(ctx.process_f32(d), want, f"compaction {kind} (2nd launch)")
     finally:
         ctx.set_filter_mode(d2pc.FILTER_CROP)
+        ctx.set_tuning("force_park", 0)
+
+
+def test_crop_finite_generic_q_and_fast(ctx):
+    import disparity_to_point_cloud_b200 as d2pc
+    q = golden("reproject_golden.npz")["q_generic"]
+    d = synth.s4_stress(200, 640, 5)
+    ctx.set_q(q)
+    ctx.set_filter_mode(d2pc.FILTER_CROP_FINITE)
+    try:
+        assert_same_bits(ctx.process_f32(d), oracle.filter_finite(oracle.disparity_cb_f32(d, q)), "generic Q")
+        q2 = _default_q().copy()
+        q2[3, 3] = 0.25  # rectified form with q33 != 0
+        ctx.set_q(q2)
+        assert_same_bits(ctx.process_f32(d), oracle.filter_finite(oracle.disparity_cb_f32(d, q2)), "q33 != 0")
+    finally:
+        ctx.set_filter_mode(d2pc.FILTER_CROP)
+        ctx.set_q(_default_q())
 
 
 # ---- device-resident batch entry ------------------------------------------------------------------
