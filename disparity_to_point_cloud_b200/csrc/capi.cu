@@ -73,7 +73,8 @@ struct d2pc_ctx {
   cudaEvent_t ev_fuse = nullptr;
   // tuning / test hooks
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0;
-  bool force_scalar = false, force_generic = false, force_park = false;
+  bool force_scalar = false, force_generic = false;
+  int compact_variant = 0;
 };
 
 namespace {
@@ -225,7 +226,7 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
   L.ctas_per_sm = ctx->ctas_per_sm;
   L.force_scalar = ctx->force_scalar;
   L.force_generic = ctx->force_generic;
-  L.force_park = ctx->force_park;
+  L.compact_variant = ctx->compact_variant;
   CU(ctx, launch_reproject(L, stream, &nl));
   ctx->launches += nl;
   return D2PC_OK;
@@ -516,7 +517,7 @@ int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value) {
   else if (k == "median_strip") ctx->median_strip = value;
   else if (k == "force_scalar") ctx->force_scalar = value != 0;
   else if (k == "force_generic") ctx->force_generic = value != 0;
-  else if (k == "force_park") ctx->force_park = value != 0;
+  else if (k == "force_park" || k == "compact_variant") ctx->compact_variant = value;
   else if (k == "median_ksize") {
     if (value < 1 || value > 15 || !(value & 1)) return D2PC_ERR_INVALID_ARG;
     ctx->cfg.median_ksize = value;

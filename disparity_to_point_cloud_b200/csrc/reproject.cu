@@ -51,6 +51,7 @@ struct ReprojArgs {
   uint32_t epoch, tiles_per_frame;
   const double *xtab, *ytab;  // (double)(float)(u + q03), (double)(float)(v + q13)
   uint32_t d_sure_bits;       // float bits of the smallest |d| whose point is certainly finite (rect0 compaction)
+  int band_rows, cw_pad, band_groups, group_rows;  // band kernel geometry
   QParams Q;
 };
 
@@ -64,6 +65,13 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
 }
 __device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void st_stream_f4_if(float4 *p, const float4 &v, bool pred) {  // predicated, no branch
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(p),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred)
+      : "memory");
 }
 
 // src/disparity_to_point_cloud.cpp:61 -- convertTo(CV_32FC1, 1/8): float(src)*alpha + 0
@@ -616,6 +624,221 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_rect0_kern
   }
 }
 
+// ---------------------------------------------------------------------------
+// CROP_FINITE, rectified Q with q33 == +-0: band kernel (the default for this Q)
+// ---------------------------------------------------------------------------
+// One CTA owns a band of R full crop rows (a contiguous range of the frame's point order):
+//   1. the band's disparities are brought into shared memory once with 16-byte cp.async (zero-filled past the
+//      crop edge, so padding classifies as "dropped" without any mask);
+//   2. every (row, 128-column) unit is classified from the disparity alone (see the classify-first kernel
+//      above for the three classes) and counted with __ballot_sync + popc -- no FP64 work yet;
+//   3. block scan of the unit counts -> unit offsets and the band total;
+//   4. ONE decoupled look-back per band (block-wide, 256 predecessors per step);
+//   5. warps sweep (segment, row-group) items: column numerators live in registers across the rows of the item,
+//      points are reprojected from shared memory and the survivors stored straight to their final place.
+// HBM traffic is exactly the algorithmic 4 B read + 16 B written per surviving point.
+constexpr int kBandMaxUnits = 512;
+constexpr int kBandMaxRows = 16;
+
+__device__ __forceinline__ void cp_async_16_zfill(void *smem_dst, const void *gmem_src, uint32_t src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+
+template <typename InT, bool kVec, int kMinB>
+__global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kernel(const __grid_constant__ ReprojArgs a) {
+  extern __shared__ __align__(16) float sd[];  // [band_rows][cw_pad]
+  __shared__ uint32_t unit_off[kBandMaxUnits];
+  __shared__ double syd[kBandMaxRows];
+  __shared__ uint32_t warp_tot[kCWarps];
+  __shared__ uint32_t lb_sum[kCWarps], lb_hit[kCWarps];
+  __shared__ uint32_t s_tile;
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const QParams &Q = a.Q;
+  const int R = a.band_rows, cwp = a.cw_pad, n_seg = a.n_seg;
+
+  if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t f = tile / a.tiles_per_frame;
+  const uint32_t t_in_f = tile - f * a.tiles_per_frame;
+  const int row0 = (int)t_in_f * R;  // first crop row of the band
+  const uint8_t *in_f = a.in + (size_t)f * a.frame_stride;
+
+  // ---- 1. band -> shared memory (columns outer, rows inner: everything but two pointers is loop-invariant)
+  const int rows_here = min(R, a.ch - row0);
+  for (int c4 = 4 * (int)threadIdx.x; c4 < cwp; c4 += 4 * kCThreads) {
+    const int left = min(max(a.cw - c4, 0), 4);  // crop pixels this 4-pixel group holds
+    float *dst = &sd[c4];
+    if constexpr (kVec && sizeof(InT) == 4) {
+      const uint8_t *src = in_f + (size_t)(a.border + row0) * a.step + (size_t)(a.border + c4) * 4;
+      if (left == 0) src = a.in;
+      for (int r = 0; r < R; ++r, dst += cwp, src += a.step)
+        cp_async_16_zfill(dst, r < rows_here ? (const void *)src : (const void *)a.in,
+                          r < rows_here ? 4u * (uint32_t)left : 0u);
+    } else {
+      for (int r = 0; r < R; ++r, dst += cwp) {
+        const uint8_t *in_row = in_f + (size_t)(a.border + row0 + r) * a.step;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_here) {
+          if (left > 0) v.x = load1<InT>(in_row, a.border + c4 + 0, a.scale);
+          if (left > 1) v.y = load1<InT>(in_row, a.border + c4 + 1, a.scale);
+          if (left > 2) v.z = load1<InT>(in_row, a.border + c4 + 2, a.scale);
+          if (left > 3) v.w = load1<InT>(in_row, a.border + c4 + 3, a.scale);
+        }
+        *reinterpret_cast<float4 *>(dst) = v;
+      }
+    }
+  }
+  if ((int)threadIdx.x < R) {  // row numerators; NaN marks a row the straight-line path must not use
+    const double y = rect_axis_const(a.border + row0 + (int)threadIdx.x, Q.q13);
+    syd[threadIdx.x] = rect_axis_slow(y) ? __longlong_as_double(0x7ff8000000000000ll) : y;
+  }
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- 2. count the survivors of every unit (unit u = r * n_seg + s).  Only the total matters here, so a lane
+  // takes four adjacent pixels (one 16-byte shared-memory load) and the warp sums with a single REDUX.
+  const int n_units = R * n_seg;
+  const uint32_t sure_lo = a.d_sure_bits, sure_span = 0x7f800000u - a.d_sure_bits;
+  for (int r = 0; r < R; ++r)
+    for (int sgm = wic; sgm < n_seg; sgm += kCWarps) {
+      const float4 d4 = *reinterpret_cast<const float4 *>(&sd[r * cwp + sgm * kSegCols + 4 * lane]);
+      const uint32_t m0 = __float_as_uint(d4.x) & 0x7fffffffu, m1 = __float_as_uint(d4.y) & 0x7fffffffu;
+      const uint32_t m2 = __float_as_uint(d4.z) & 0x7fffffffu, m3 = __float_as_uint(d4.w) & 0x7fffffffu;
+      // sure class: d_sure <= |d| < inf
+      uint32_t cnt = ((m0 - sure_lo) < sure_span) + ((m1 - sure_lo) < sure_span) + ((m2 - sure_lo) < sure_span) +
+                     ((m3 - sure_lo) < sure_span);
+      // sliver class: 0 < |d| < d_sure -- decided exactly, rare
+      const bool s0 = (m0 - 1u) < (sure_lo - 1u), s1 = (m1 - 1u) < (sure_lo - 1u);
+      const bool s2 = (m2 - 1u) < (sure_lo - 1u), s3 = (m3 - 1u) < (sure_lo - 1u);
+      if (__builtin_expect(s0 || s1 || s2 || s3, 0)) {
+        const int u = a.border + sgm * kSegCols + 4 * lane, v = a.border + row0 + r;
+        if (s0) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 0, v, d4.x)) ? 1u : 0u;
+        if (s1) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 1, v, d4.y)) ? 1u : 0u;
+        if (s2) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 2, v, d4.z)) ? 1u : 0u;
+        if (s3) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 3, v, d4.w)) ? 1u : 0u;
+      }
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (lane == 0) unit_off[r * n_seg + sgm] = cnt;
+    }
+  __syncthreads();
+  // ---- 3. exclusive scan of the unit counts (two entries per thread)
+  uint32_t band_total;
+  {
+    const int i0 = 2 * (int)threadIdx.x;
+    const uint32_t c0 = i0 < n_units ? unit_off[i0] : 0u, c1 = i0 + 1 < n_units ? unit_off[i0 + 1] : 0u;
+    uint32_t incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[wic] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kCWarps; ++w) {
+      const uint32_t t = warp_tot[w];
+      wbase += (w < wic) ? t : 0u;
+      tot += t;
+    }
+    band_total = tot;
+    const uint32_t e0 = wbase + incl - (c0 + c1);
+    if (i0 < n_units) unit_off[i0] = e0;
+    if (i0 + 1 < n_units) unit_off[i0 + 1] = e0 + c0;
+  }
+  // ---- 4. decoupled look-back, block-wide; the first band of a frame starts the chain
+  unsigned long long *desc = a.tile_desc + tile;
+  uint32_t excl = 0;
+  if (t_in_f == 0) {
+    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, band_total));
+    __syncthreads();  // unit_off complete before step 5
+  } else {
+    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagAggregate, band_total));
+    int look = (int)t_in_f - 1;
+    for (;;) {
+      const int my = look - (int)threadIdx.x;
+      uint32_t flag = kFlagPrefix, val = 0;  // positions before the frame start act as a zero prefix
+      if (my >= 0) {
+        unsigned long long dv;
+        do {
+          dv = ld_relaxed_u64(a.tile_desc + (tile - t_in_f) + my);
+        } while ((uint32_t)(dv >> 34) != a.epoch || ((dv >> 32) & 3u) == 0);
+        flag = (uint32_t)(dv >> 32) & 3u;
+        val = (uint32_t)dv;
+      }
+      const uint32_t pmask = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
+      const int stop = pmask ? (__ffs(pmask) - 1) : 32;
+      uint32_t contrib = (lane <= stop) ? val : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+      if (lane == 0) lb_sum[wic] = contrib, lb_hit[wic] = pmask ? 1u : 0u;
+      __syncthreads();
+      bool done = false;
+#pragma unroll
+      for (int w = 0; w < kCWarps; ++w) {
+        if (!done) {
+          excl += lb_sum[w];
+          done = lb_hit[w] != 0u;
+        }
+      }
+      if (done) break;
+      look -= kCThreads;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, excl + band_total));
+  }
+  if (threadIdx.x == 0 && t_in_f == a.tiles_per_frame - 1 && a.counts) a.counts[f] = excl + band_total;
+
+  // ---- 5. reproject + store: item = (segment, row group); column numerators stay in registers over its rows
+  float4 *out_f = a.out + (size_t)f * a.out_frame_stride + excl;
+  const int n_items = n_seg * a.band_groups;
+  for (int item = wic; item < n_items; item += kCWarps) {
+    const int g = item / n_seg, sgm = item - g * n_seg;
+    const int r_lo = g * a.group_rows, r_hi = min(r_lo + a.group_rows, R);
+    const int u0 = a.border + sgm * kSegCols + lane;
+    double xd[4];
+    uint32_t xslow = Q.zd_slow ? 0xfu : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xd[k] = rect_axis_const(u0 + 32 * k, Q.q03);
+      xslow |= rect_axis_slow(xd[k]) ? (1u << k) : 0u;
+    }
+    for (int r = r_lo; r < r_hi; ++r) {
+      const double yd = syd[r];
+      const bool yslow = ((uint32_t)__double2hiint(yd) & 0x7ff00000u) == 0x7ff00000u;
+      const float *dp = &sd[r * cwp + sgm * kSegCols + lane];
+      float dd[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dd[k] = dp[32 * k];
+      float4 p[4];
+      points_of4<kMathRect0>(Q, xd, yd, xslow, yslow, u0, a.border + row0 + r, dd, p);
+      // same three classes as step 2: sure -> kept, zero / inf / NaN -> dropped, sliver -> exact (rare)
+      bool kp[4], any_sliver = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t mag = __float_as_uint(dd[k]) & 0x7fffffffu;
+        kp[k] = (mag - sure_lo) < sure_span;
+        any_sliver |= (mag - 1u) < (sure_lo - 1u);
+      }
+      if (__builtin_expect(any_sliver, 0)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (((__float_as_uint(dd[k]) & 0x7fffffffu) - 1u) < (sure_lo - 1u)) kp[k] = point_is_finite(p[k]);
+      }
+      uint32_t pos = unit_off[r * n_seg + sgm];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, kp[k]);
+        st_stream_f4_if(out_f + (uint32_t)(pos + __popc(bal & lt_mask)), p[k], kp[k]);
+        pos += __popc(bal);
+      }
+    }
+  }
+}
+
 template <typename K>
 cudaError_t launch_compact(K kernel, const ReprojArgs &a, int grid, cudaStream_t s) {
   // 52 KB of dynamic shared memory needs the opt-in on every instantiation (and on every device)
@@ -629,6 +852,18 @@ template <typename InT, int kMath>
 cudaError_t launch_typed(const ReprojArgs &a, bool vec, bool compact, int grid, int min_blocks, cudaStream_t s) {
   if (compact) {
     if constexpr (kMath == kMathRect0) {
+      if (a.d_sure_bits != 0 && a.band_rows > 0) {  // band kernel
+        const size_t smem = (size_t)a.band_rows * a.cw_pad * sizeof(float);
+        auto kern = !vec ? reproject_compact_band_kernel<InT, false, 3>
+                         : (min_blocks == 3 ? reproject_compact_band_kernel<InT, true, 3>
+                                            : reproject_compact_band_kernel<InT, true, 4>);
+        if (smem > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, kCThreads, smem, s>>>(a);
+        return cudaGetLastError();
+      }
       if (a.d_sure_bits != 0) {  // classify-first kernel
         if (!vec)
           reproject_compact_rect0_kernel<InT, false, 3><<<grid, kCThreads, 0, s>>>(a);
@@ -701,7 +936,8 @@ static uint64_t compact_tiles_per_frame(long cw, long ch) {
 // tile descriptors (must start zeroed: epoch 0 means "never written")
 size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border) {
   const long cw = (long)width - 2L * border, ch = (long)height - 2L * border;
-  const uint64_t tiles = (cw > 0 && ch > 0) ? compact_tiles_per_frame(cw, ch) : 0;
+  // enough for either tiling: 32-unit tiles (park / classify-first kernels) or row bands (band kernel)
+  const uint64_t tiles = (cw > 0 && ch > 0) ? std::max<uint64_t>(compact_tiles_per_frame(cw, ch), (uint64_t)ch) : 0;
   return (size_t)(tiles * n_frames * 8 + 256);
 }
 // per-column / per-row numerator tables of the rectified path
@@ -762,7 +998,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
     grid = (int)total;  // one CTA per tile; the ticket, not blockIdx, names the tile
     cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    if (math == kMathRect0 && !a.Q.zd_slow && !L.force_park) {
+    if (math == kMathRect0 && !a.Q.zd_slow && L.compact_variant != 1) {
       // |n| <= max_numer for every numerator of the frame; |q| = |n| / (|q32| * |d|) < 2^127 once
       // |d| >= max_numer * 2^-127 / |q32|; doubled for margin, clamped to the smallest normal float.
       const double aq32 = a.Q.q32 < 0 ? -a.Q.q32 : a.Q.q32;
@@ -778,7 +1014,32 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
         memcpy(&a.d_sure_bits, &fs, 4);
       }
     }
-    if (a.Q.rectified && !L.arith_fast && !L.force_generic) {
+    if (a.d_sure_bits != 0 && L.compact_variant == 0) {
+      // band geometry: R rows per CTA (<= ~46 KB of disparities, <= 512 units), split into row groups so that
+      // (segments x groups) fills the 8 warps evenly
+      a.cw_pad = a.n_seg * kSegCols;
+      const size_t row_bytes = (size_t)a.cw_pad * sizeof(float);
+      int r_max = (int)std::min<size_t>((46 * 1024) / row_bytes, (size_t)kBandMaxRows);
+      r_max = std::min(r_max, kBandMaxUnits / a.n_seg);
+      if (r_max < 1 && row_bytes <= 200 * 1024 && a.n_seg <= kBandMaxUnits) r_max = 1;
+      if (r_max > (int)ch) r_max = (int)ch;
+      double best = -1.0;
+      for (int r = r_max; r >= 1 && r >= r_max - 3; --r)
+        for (int g = 1; g <= r; ++g) {
+          const int gr = (r + g - 1) / g, ga = (r + gr - 1) / gr;
+          const int items = a.n_seg * ga;
+          const double eff = (double)items / (kCWarps * ((items + kCWarps - 1) / kCWarps));
+          const double score = eff * (gr / (gr + 0.6)) * (r / (r + 0.5));
+          if (score > best + 1e-9) best = score, a.band_rows = r, a.band_groups = ga, a.group_rows = gr;
+        }
+      if (a.band_rows > 0) {
+        a.tiles_per_frame = (uint32_t)((ch + a.band_rows - 1) / a.band_rows);
+        const uint64_t total_b = (uint64_t)a.tiles_per_frame * L.n_frames;
+        if (total_b > 0xffffffffull) return cudaErrorInvalidValue;
+        grid = (int)total_b;
+      }
+    }
+    if (a.Q.rectified && !L.arith_fast && !L.force_generic && a.band_rows == 0) {
       const int n = (int)(L.width + kSegCols > L.height ? L.width + kSegCols : L.height);
       rect_tables_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a.Q.q03, a.Q.q13, (int)L.width, (int)L.height, tabs,
                                                             tabs + L.width + kSegCols);

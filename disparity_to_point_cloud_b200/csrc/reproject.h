@@ -44,7 +44,7 @@ struct ReprojectLaunch {
   int ctas_per_sm = 0;
   bool force_scalar = false;   // exercise the unaligned load path
   bool force_generic = false;  // exercise the generic-Q exact path on a rectified Q
-  bool force_park = false;     // CROP_FINITE: use the park-then-compact kernel even where classify-first applies
+  int compact_variant = 0;     // CROP_FINITE kernel: 0 = automatic (band), 1 = park-then-compact, 2 = classify-first
 };
 
 void make_qparams(const double q[16], QParams *out);

@@ -16,7 +16,7 @@ d_in = torch.stack([torch.roll(base, 17 * i, dims=1) for i in range(f)]).contigu
 d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
 d_cnt = torch.zeros(f, dtype=torch.int32, device="cuda")
 ctx.set_filter_mode(1)
-for park in (0, 0, 1, 1):
+for park in (0, 0, 0):
     ctx.set_tuning("force_park", park)
     ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4, d_out.data_ptr(), n * 16, d_cnt.data_ptr())
 ctx.sync()
