@@ -122,13 +122,8 @@ def barrier_sync(world):
 
 
 def max_over_ranks(x, world):
-    import torch
-    import torch.distributed as dist
-    if world == 1:
-        return x
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from disparity_to_point_cloud_b200 import sharding
+    return sharding.max_over_ranks(x, device="cuda") if world > 1 else x
 
 
 def cpu_port_run(n_frames, threads, repeat=1):
@@ -189,8 +184,13 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
-    frames_per_step = args.frames
-    ring = min(RING, frames_per_step)
+    from disparity_to_point_cloud_b200 import sharding
+    # frames are independent: weak = every rank runs args.frames frames per step, strong = args.frames are
+    # sharded i mod G (BASELINE configs[3] wording); no data-path collective either way
+    per_rank = sharding.frames_per_rank(args.frames, world, args.scaling)
+    frames_per_step = per_rank[rank]
+    total_frames_per_step = sum(per_rank)
+    ring = min(RING, max(frames_per_step, 1))
     launches_per_step = (frames_per_step + ring - 1) // ring
 
     ctx = d2pc.Context(device=local, n_slots=3)
@@ -229,7 +229,7 @@ def run_ours(args):
     launches = ctx.launch_count() - l0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1), world)
     ms_step = ms_total / args.steps
-    value = world * frames_per_step * W * H / (ms_step / 1e3) / 1e6
+    value = total_frames_per_step * W * H / (ms_step / 1e3) / 1e6
 
     # one frame checked on the device path so a broken kernel can not post a number
     probe = d_out[1, :64].cpu().numpy().view(np.float32)
@@ -250,6 +250,7 @@ def run_ours(args):
 
     # ---- end to end: pinned host frames -> H2D -> kernel -> D2H, through d2pc_process_stream
     e2e_frames = args.e2e_frames if args.e2e_frames > 0 else frames_per_step
+    e2e_total = sharding.sum_over_ranks(e2e_frames, device="cuda") if world > 1 else e2e_frames
     host_ring = 8
     pin = d2pc.PinnedArray((host_ring, H, W), np.float32)
     hb = synth.s3_float(H, W, 1000 * rank + 1)
@@ -271,11 +272,11 @@ def run_ours(args):
     e2e_step(e2e_frames)
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-    e2e_value = world * e2e_frames * W * H / e2e_s / 1e6
+    e2e_value = e2e_total * W * H / e2e_s / 1e6
     assert checks.get("width") == N_PTS
     e2e = {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": frames_per_step * W * H * 4,
            "d2h_bytes_per_step": frames_per_step * N_PTS * 16, "frames_timed": e2e_frames,
-           "frames_per_s": world * e2e_frames / e2e_s, "timer": "wall clock between device syncs, max over ranks"}
+           "frames_per_s": e2e_total / e2e_s, "timer": "wall clock between device syncs, max over ranks"}
     pin.free()
 
     cpu_baseline = None
@@ -294,14 +295,15 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3840x2160 float32 disparity (S3), %d frames per GPU per step, reproject+crop+pack "
                                    "(BASELINE configs[3])" % frames_per_step,
                        "frames_per_step_per_gpu": frames_per_step, "resident_ring_frames": ring,
                        "l2_policy": "inputs+outputs of one launch are 2.5 GB (>> 126 MB L2), no flush needed",
                        "arith": "EXACT (bit-identical to cv::reprojectImageTo3D)", "filter": "CROP (reference)",
-                       "frames_per_s": world * frames_per_step / (ms_step / 1e3)},
+                       "frames_per_s": total_frames_per_step / (ms_step / 1e3),
+                       "sharding": "frame i -> rank i mod G, no collective on the data path"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "extras": extras,
         }
@@ -390,6 +392,8 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP, help="frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=0, help="frames timed end to end (0 = one full step)")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --frames per GPU per step; strong: --frames in total, sharded i mod G")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

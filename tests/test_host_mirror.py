@@ -1,0 +1,79 @@
+"""The C++ host mirror (include/d2pc_b200/nodes.hpp) driven through tools/d2pc_offline:
+Disparity2PCloud::DisparityCb and DepthMapFusion's callbacks behind the reference's topic names and the
+launch-file remaps, ROS1 wire bytes in and out."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT, golden
+from disparity_to_point_cloud_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def harness():
+    from disparity_to_point_cloud_b200 import build
+    build.build()
+    return build.build_harness()
+
+
+def image_msg(img, sec, nsec, seq=0, frame_id="camera"):
+    h, w = img.shape
+    fid = frame_id.encode()
+    return (struct.pack("<III", seq, sec, nsec) + struct.pack("<I", len(fid)) + fid + struct.pack("<II", h, w) +
+            struct.pack("<I", 5) + b"mono8" + struct.pack("<BI", 0, w) + struct.pack("<I", w * h) + img.tobytes())
+
+
+def test_wire_selftest(harness, tmp_path):
+    out = tmp_path / "wire.bin"
+    subprocess.run([harness, "wire", str(out)], check=True)
+    assert out.read_bytes() == oracle.serialize_pointcloud2(np.arange(32, dtype=np.uint8), seq=7, sec=11, nsec=13)
+
+
+def test_launch_files_keep_the_reference_remaps():
+    d2p = open(os.path.join(ROOT, "launch", "d2pcloud.launch")).read()
+    assert 'from="/disparity" to="/throttled_depth_map"' in d2p and 'from="/point_cloud" to="/omi_cam/point_cloud"' in d2p
+    assert 'type="disparity_to_point_cloud_node"' in d2p
+    fus = open(os.path.join(ROOT, "launch", "depth_map_fusion.launch")).read()
+    for a, b in [("/matching_score_1", "cam_0"), ("/disparity_1", "cam_1"), ("/matching_score_2", "cam_2"),
+                 ("/disparity_2", "cam_3")]:
+        assert f'from="{a}" to="/uvc_camera/{b}/image_raw"' in fus
+    assert 'name="offset_x" value="-7"' in fus and 'name="offset_y" value="15"' in fus
+
+
+@pytest.mark.gpu
+def test_node1_disparity_cb_through_launch_remaps(harness, tmp_path):
+    q = golden("q_golden.npz")["q"][0]
+    img = synth.s2_scene(480, 752, 21)
+    raw, out = tmp_path / "in.raw", tmp_path / "cloud.bin"
+    raw.write_bytes(img.tobytes())
+    subprocess.run([harness, "node1", os.path.join(ROOT, "launch", "d2pcloud.launch"), "752", "480", str(raw), str(out),
+                    "1700000000", "250"], check=True)
+    want = oracle.serialize_pointcloud2(oracle.disparity_cb_mono8(img, q), seq=0, sec=1700000000, nsec=250)
+    assert out.read_bytes() == want
+
+
+@pytest.mark.gpu
+def test_fusion_node_then_node1_config5(harness, tmp_path):
+    q = golden("q_golden.npz")["q"][0]
+    h, w = 720, 1280
+    rng = np.random.default_rng(9)
+    d1, d2 = synth.s2_scene(h, w, 31), synth.s2_scene(h, w, 32)
+    s1 = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    s2 = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    paths = []
+    for name, a in (("d1", d1), ("d2", d2), ("s1", s1), ("s2", s2)):
+        p = tmp_path / f"{name}.raw"
+        p.write_bytes(a.tobytes())
+        paths.append(str(p))
+    fused_bin, cloud_bin = tmp_path / "fused.bin", tmp_path / "cloud.bin"
+    subprocess.run([harness, "fusion", os.path.join(ROOT, "launch", "depth_map_fusion.launch"), str(w), str(h)] + paths +
+                   [str(fused_bin), str(cloud_bin)], check=True)
+    fused, _ = oracle.fuse(d1, d2, s1, s2, -7, 15)
+    assert fused.shape == (665, 665)
+    assert fused_bin.read_bytes() == image_msg(fused, 2, 500)          # header of message 2 (:134-135)
+    want = oracle.serialize_pointcloud2(oracle.disparity_cb_mono8(fused, q), seq=0, sec=2, nsec=500)
+    assert cloud_bin.read_bytes() == want
