@@ -105,6 +105,12 @@ SYMBOLS = [
     ("d2pc_fuse_geometry", C.c_int, [_ctx, C.c_uint32, C.c_uint32, _i32p, _i32p, _i32p, _i32p]),
     ("d2pc_fuse", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                             C.c_uint32, C.POINTER(Image), C.POINTER(Image)]),
+    ("d2pc_preprocess_score", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                        C.POINTER(Image)]),
+    ("d2pc_preprocess_score_device", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int,
+                                               C.c_void_p]),
+    ("d2pc_fuse_preprocessed", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                         C.c_uint32, C.POINTER(Image), C.POINTER(Image)]),
     ("d2pc_fuse_device", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                    C.c_size_t, C.c_void_p, C.c_void_p]),
     ("d2pc_fuse_then_process", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
@@ -338,6 +344,24 @@ class Context:
         fused, combined = Image(), Image()
         self._check(lib().d2pc_fuse(self._h, *(a.ctypes.data for a in arrs), w, h, w, C.byref(fused),
                                     C.byref(combined)), "d2pc_fuse")
+        return fused.array().copy(), combined.array().copy()
+
+    def preprocess_score(self, score, which: int) -> np.ndarray:
+        a = np.ascontiguousarray(score, dtype=np.uint8)
+        h, w = a.shape
+        out = Image()
+        self._check(lib().d2pc_preprocess_score(self._h, a.ctypes.data, w, h, w, which, C.byref(out)),
+                    "d2pc_preprocess_score")
+        return out.array().copy()
+
+    def fuse_preprocessed(self, d1, d2, s1c, s2c):
+        d1, d2 = (np.ascontiguousarray(a, dtype=np.uint8) for a in (d1, d2))
+        s1c, s2c = (np.ascontiguousarray(a, dtype=np.uint8) for a in (s1c, s2c))
+        h, w = d1.shape
+        fused, combined = Image(), Image()
+        self._check(lib().d2pc_fuse_preprocessed(self._h, d1.ctypes.data, d2.ctypes.data, s1c.ctypes.data,
+                                                 s2c.ctypes.data, w, h, w, C.byref(fused), C.byref(combined)),
+                    "d2pc_fuse_preprocessed")
         return fused.array().copy(), combined.array().copy()
 
     def fuse_device(self, d_d1, d_d2, d_s1, d_s2, w, h, step, d_fused, d_combined=0):

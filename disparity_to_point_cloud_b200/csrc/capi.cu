@@ -11,6 +11,7 @@
 // the CUDA kernels or returns an error.
 #include "../../include/d2pc_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +23,7 @@
 #include "fusion.h"
 #include "median.h"
 #include "reproject.h"
+#include "score.h"
 
 using namespace d2pc;
 
@@ -70,6 +72,8 @@ struct d2pc_ctx {
   // fusion buffers
   DevBuf d_fuse_in[4], d_container, d_combined, d_fused;
   PinBuf h_fused, h_combined;
+  DevBuf d_score_in, d_score_scratch, d_score_out[2];
+  PinBuf h_score[2];
   cudaEvent_t ev_fuse = nullptr;
   // tuning / test hooks
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0;
@@ -479,6 +483,8 @@ void d2pc_destroy(d2pc_ctx *ctx) {
   for (auto &b : ctx->d_fuse_in) free_dev(b);
   free_dev(ctx->d_container), free_dev(ctx->d_combined), free_dev(ctx->d_fused);
   free_pin(ctx->h_fused), free_pin(ctx->h_combined);
+  free_dev(ctx->d_score_in), free_dev(ctx->d_score_scratch), free_dev(ctx->d_score_out[0]), free_dev(ctx->d_score_out[1]);
+  free_pin(ctx->h_score[0]), free_pin(ctx->h_score[1]);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->ev_fuse) cudaEventDestroy(ctx->ev_fuse);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -724,7 +730,7 @@ int d2pc_fuse_geometry(const d2pc_ctx *ctx, uint32_t w, uint32_t h, int rect1[4]
 
 static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1, const uint8_t *s2,
                             uint32_t w, uint32_t h, size_t step, uint8_t *d_fused, uint8_t *d_combined,
-                            FuseGeometry *g_out) {
+                            FuseGeometry *g_out, bool scores_cropped = false) {
   const d2pc_config &c = ctx->cfg;
   FuseGeometry g;
   if (!fuse_geometry((int)w, (int)h, c.offset_x, c.offset_y, c.fuse_crop_left, c.fuse_crop_right, c.fuse_crop_top,
@@ -741,6 +747,7 @@ static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2,
   L.width = (int)w, L.height = (int)h;
   L.g = g;
   L.rule = c.fuse_rule;
+  L.scores_cropped = scores_cropped;
   L.container = ctx->d_container.p;
   L.combined = d_combined;
   int nl = 0;
@@ -810,6 +817,118 @@ int d2pc_fuse(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t
                           ctx->s_compute));
   CU(ctx, cudaMemcpyAsync(ctx->h_combined.p, ctx->d_combined.p, (size_t)g.n * g.n, cudaMemcpyDeviceToHost,
                           ctx->s_compute));
+  CU(ctx, cudaStreamSynchronize(ctx->s_compute));
+  fused->data = ctx->h_fused.p;
+  fused->width = (uint32_t)g.out_w, fused->height = (uint32_t)g.out_h, fused->step = (uint32_t)g.out_w;
+  if (combined) {
+    combined->data = ctx->h_combined.p;
+    combined->width = combined->height = combined->step = (uint32_t)g.n;
+  }
+  return D2PC_OK;
+}
+
+// ---- matching-score preprocessing -----------------------------------------------------------------------
+static int score_device_impl(d2pc_ctx *ctx, const uint8_t *d_score, uint32_t w, uint32_t h, size_t step, int which,
+                             uint8_t *d_out, int *n_out) {
+  const d2pc_config &c = ctx->cfg;
+  FuseGeometry g;
+  if (!fuse_geometry((int)w, (int)h, c.offset_x, c.offset_y, c.fuse_crop_left, c.fuse_crop_right, c.fuse_crop_top,
+                     c.fuse_crop_bottom, &g))
+    return D2PC_ERR_GEOMETRY;
+  const int n = g.n;
+  int rc;
+  const size_t need = score_scratch_bytes(n);
+  if (need > ctx->d_score_scratch.cap) {
+    CU(ctx, cudaStreamSynchronize(ctx->s_compute));
+    if ((rc = grow_dev(ctx, ctx->d_score_scratch, need))) return rc;
+  }
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  ScoreLaunch L;
+  L.frame = d_score;
+  L.step = step;
+  L.width = (int)w, L.height = (int)h;
+  L.rotated = which == 2;
+  const int *r = which == 2 ? g.r2 : g.r1;  // :66 cropToSquare(image, ox, oy) / :85 cropToSquare(rot, -ox, -oy)
+  for (int i = 0; i < 4; ++i) L.rect[i] = r[i];
+  uint8_t *p = ctx->d_score_scratch.p;
+  L.rows16 = reinterpret_cast<uint16_t *>(p);
+  p += al((size_t)(n + 20) * n * 2);
+  L.f32 = reinterpret_cast<float *>(p);
+  p += al((size_t)n * n * 4);
+  L.tmp8a = p;
+  p += al((size_t)n * n);
+  L.tmp8b = p;
+  L.out = d_out;
+  int nl = 0;
+  CU(ctx, launch_score_preprocess(L, ctx->s_compute, &nl));
+  ctx->launches += nl;
+  if (n_out) *n_out = n;
+  return D2PC_OK;
+}
+
+int d2pc_preprocess_score_device(d2pc_ctx *ctx, const uint8_t *d_score, uint32_t w, uint32_t h, size_t step, int which,
+                                 uint8_t *d_out) {
+  if (!ctx || !d_score || !d_out || (which != 1 && which != 2)) return D2PC_ERR_INVALID_ARG;
+  if (w == 0 || h == 0 || step < w) return D2PC_ERR_BAD_DIMS;
+  CU(ctx, cudaSetDevice(ctx->device));
+  return score_device_impl(ctx, d_score, w, h, step, which, d_out, nullptr);
+}
+
+int d2pc_preprocess_score(d2pc_ctx *ctx, const uint8_t *score, uint32_t w, uint32_t h, uint32_t step, int which,
+                          d2pc_image *out) {
+  if (!ctx || !score || !out || (which != 1 && which != 2)) return D2PC_ERR_INVALID_ARG;
+  if (w == 0 || h == 0 || step < w) return D2PC_ERR_BAD_DIMS;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->s_compute));
+  int rc;
+  const size_t pitch = align_up(w, kAlign);
+  const size_t side = (size_t)(w < h ? w : h);
+  DevBuf &d_out = ctx->d_score_out[which - 1];
+  PinBuf &h_out = ctx->h_score[which - 1];
+  if ((rc = grow_dev(ctx, ctx->d_score_in, pitch * h)) || (rc = grow_dev(ctx, d_out, side * side)) ||
+      (rc = grow_pin(ctx, h_out, side * side)))
+    return rc;
+  CU(ctx, cudaMemcpy2DAsync(ctx->d_score_in.p, pitch, score, step, w, h, cudaMemcpyHostToDevice, ctx->s_compute));
+  int n = 0;
+  if ((rc = score_device_impl(ctx, ctx->d_score_in.p, w, h, pitch, which, d_out.p, &n))) return rc;
+  CU(ctx, cudaMemcpyAsync(h_out.p, d_out.p, (size_t)n * n, cudaMemcpyDeviceToHost, ctx->s_compute));
+  CU(ctx, cudaStreamSynchronize(ctx->s_compute));
+  out->data = h_out.p;
+  out->width = out->height = out->step = (uint32_t)n;
+  return D2PC_OK;
+}
+
+int d2pc_fuse_preprocessed(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1c, const uint8_t *s2c,
+                           uint32_t w, uint32_t h, uint32_t step, d2pc_image *fused, d2pc_image *combined) {
+  if (!ctx || !d1 || !d2 || !s1c || !s2c || !fused) return D2PC_ERR_INVALID_ARG;
+  if (w == 0 || h == 0 || step < w) return D2PC_ERR_BAD_DIMS;
+  const d2pc_config &c = ctx->cfg;
+  FuseGeometry g;
+  if (!fuse_geometry((int)w, (int)h, c.offset_x, c.offset_y, c.fuse_crop_left, c.fuse_crop_right, c.fuse_crop_top,
+                     c.fuse_crop_bottom, &g))
+    return D2PC_ERR_GEOMETRY;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->s_compute));
+  int rc;
+  const size_t pitch = align_up(w, kAlign), nn = (size_t)g.n * g.n;
+  const size_t side = (size_t)(w < h ? w : h);
+  for (int i = 0; i < 2; ++i)
+    if ((rc = grow_dev(ctx, ctx->d_fuse_in[i], pitch * h))) return rc;
+  for (int i = 2; i < 4; ++i)
+    if ((rc = grow_dev(ctx, ctx->d_fuse_in[i], std::max(pitch * h, nn)))) return rc;
+  if ((rc = grow_dev(ctx, ctx->d_fused, side * side)) || (rc = grow_dev(ctx, ctx->d_combined, side * side)) ||
+      (rc = grow_pin(ctx, ctx->h_fused, (size_t)g.out_w * g.out_h)) || (rc = grow_pin(ctx, ctx->h_combined, nn)))
+    return rc;
+  CU(ctx, cudaMemcpy2DAsync(ctx->d_fuse_in[0].p, pitch, d1, step, w, h, cudaMemcpyHostToDevice, ctx->s_compute));
+  CU(ctx, cudaMemcpy2DAsync(ctx->d_fuse_in[1].p, pitch, d2, step, w, h, cudaMemcpyHostToDevice, ctx->s_compute));
+  CU(ctx, cudaMemcpyAsync(ctx->d_fuse_in[2].p, s1c, nn, cudaMemcpyHostToDevice, ctx->s_compute));
+  CU(ctx, cudaMemcpyAsync(ctx->d_fuse_in[3].p, s2c, nn, cudaMemcpyHostToDevice, ctx->s_compute));
+  rc = fuse_device_impl(ctx, ctx->d_fuse_in[0].p, ctx->d_fuse_in[1].p, ctx->d_fuse_in[2].p, ctx->d_fuse_in[3].p, w, h,
+                        pitch, ctx->d_fused.p, ctx->d_combined.p, nullptr, /*scores_cropped=*/true);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpyAsync(ctx->h_fused.p, ctx->d_fused.p, (size_t)g.out_w * g.out_h, cudaMemcpyDeviceToHost,
+                          ctx->s_compute));
+  CU(ctx, cudaMemcpyAsync(ctx->h_combined.p, ctx->d_combined.p, nn, cudaMemcpyDeviceToHost, ctx->s_compute));
   CU(ctx, cudaStreamSynchronize(ctx->s_compute));
   fused->data = ctx->h_fused.p;
   fused->width = (uint32_t)g.out_w, fused->height = (uint32_t)g.out_h, fused->step = (uint32_t)g.out_w;

@@ -24,6 +24,7 @@ struct FuseArgs {
   int width, height;
   int x1, y1, x2, y2, xc, yc, n, nc;
   int rule;
+  int scores_cropped;  // s1 / s2 are n x n dense images already in merge coordinates (preprocessed caches)
   uint8_t *container, *combined;
 };
 
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) fuse_merge_kernel(const __grid_constant__
       if (j < a.n && i < a.n) {
         const size_t off = (size_t)(a.height - 1 - (a.x2 + j)) * a.step + (size_t)(a.y2 + i);
         t_d2[ty + 8 * m][tx] = a.d2[off];
-        t_s2[ty + 8 * m][tx] = a.s2[off];
+        if (!a.scores_cropped) t_s2[ty + 8 * m][tx] = a.s2[off];
       }
     }
   }
@@ -81,8 +82,9 @@ __global__ void __launch_bounds__(256) fuse_merge_kernel(const __grid_constant__
     int out;
     if (i < a.n && j < a.n) {
       const size_t o1 = (size_t)(a.y1 + i) * a.step + (size_t)(a.x1 + j);
-      const int d1 = a.d1[o1], s1 = a.s1[o1];
-      const int d2 = t_d2[tx][ty + 8 * m], s2 = t_s2[tx][ty + 8 * m];
+      const int d1 = a.d1[o1], d2 = t_d2[tx][ty + 8 * m];
+      const int s1 = a.scores_cropped ? a.s1[(size_t)i * a.n + j] : a.s1[o1];
+      const int s2 = a.scores_cropped ? a.s2[(size_t)i * a.n + j] : t_s2[tx][ty + 8 * m];
       out = fuse_rule(a.rule, d1, d2, s1, s2);
       // :118-121 -- score_1 == grad_1 == combined alias one buffer (:77, :113): min of the values read above
       if (a.combined) a.combined[(size_t)i * a.n + j] = (uint8_t)min(s1, s2);
@@ -141,6 +143,7 @@ cudaError_t launch_fuse_merge(const FuseLaunch &L, cudaStream_t stream, int *lau
   a.xc = L.g.rc[0], a.yc = L.g.rc[1];
   a.n = L.g.n, a.nc = L.g.nc;
   a.rule = L.rule;
+  a.scores_cropped = L.scores_cropped ? 1 : 0;
   a.container = L.container;
   a.combined = L.combined;
   const dim3 grid((a.nc + kTile - 1) / kTile, (a.nc + kTile - 1) / kTile);

@@ -22,6 +22,7 @@ struct FuseLaunch {
   int width, height;
   FuseGeometry g;
   int rule;
+  bool scores_cropped = false;  // s1 / s2 are n x n dense preprocessed scores (merge coordinates)
   uint8_t *container;  // device, nc x nc dense: merge output before the median
   uint8_t *combined;   // device, n x n dense, or nullptr
 };

@@ -1,0 +1,24 @@
+// score.h -- host-side interface of score.cu (matching-score preprocessing of depth_map_fusion)
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace d2pc {
+
+struct ScoreLaunch {
+  const uint8_t *frame = nullptr;  // device, mono8 score frame as received (w x h, `step` bytes per row)
+  size_t step = 0;
+  int width = 0, height = 0;
+  bool rotated = false;  // true for score 2: the chain runs on rotateMat(frame) (90 deg clockwise, h cols x w rows)
+  int rect[4] = {0, 0, 0, 0};  // cropToSquare rectangle {x, y, n, n} in the (rotated) frame
+  // scratch (device): rows16 >= (n + 20) * n * 2 bytes, f32 >= n * n * 4 bytes, tmp8a / tmp8b >= n * n bytes
+  uint16_t *rows16 = nullptr;
+  float *f32 = nullptr;
+  uint8_t *tmp8a = nullptr, *tmp8b = nullptr;
+  uint8_t *out = nullptr;  // device, n x n dense: what the node caches as cropped_score_k_
+};
+size_t score_scratch_bytes(int n);  // total for rows16 + f32 + tmp8a + tmp8b, each 256-byte aligned
+cudaError_t launch_score_preprocess(const ScoreLaunch &L, cudaStream_t stream, int *launches);
+
+}  // namespace d2pc

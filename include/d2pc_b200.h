@@ -232,6 +232,23 @@ int d2pc_fuse_geometry(const d2pc_ctx *ctx, uint32_t width, uint32_t height, int
 int d2pc_fuse(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1, const uint8_t *s2,
               uint32_t width, uint32_t height, uint32_t step, d2pc_image *fused, d2pc_image *combined);
 
+/* MatchingScoreCb1 (which = 1, src/depth_map_fusion.cpp:64-80) / MatchingScoreCb2 (which = 2, :82-99) on one
+ * mono8 score frame in host memory: [rotate for 2 ->] cropToSquare -> GaussianBlur 13 sigma 3 -> Sobel 2nd
+ * derivative ksize 7 x0.03 -> threshold 30 -> GaussianBlur 21 sigma 10 -> score + 2*grad (saturating).
+ * out is the n x n image the node caches as cropped_score_k_ (library-owned pinned memory, one buffer per
+ * `which`, valid until the next call with the same `which`). */
+int d2pc_preprocess_score(d2pc_ctx *ctx, const uint8_t *score, uint32_t width, uint32_t height, uint32_t step,
+                          int which, d2pc_image *out);
+/* Same with device pointers; d_out is n x n dense. */
+int d2pc_preprocess_score_device(d2pc_ctx *ctx, const uint8_t *d_score, uint32_t width, uint32_t height, size_t step,
+                                 int which, uint8_t *d_out);
+
+/* d2pc_fuse with the two score inputs given as the n x n preprocessed caches (d2pc_preprocess_score output)
+ * instead of full frames: exactly the state publishFusedDepthMap works from. */
+int d2pc_fuse_preprocessed(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1_cropped,
+                           const uint8_t *s2_cropped, uint32_t width, uint32_t height, uint32_t step,
+                           d2pc_image *fused, d2pc_image *combined);
+
 /* Same, device pointers, enqueued on the compute stream.  d_fused is
  * fused_w x fused_h dense; d_combined n x n dense (may be NULL). */
 int d2pc_fuse_device(d2pc_ctx *ctx, const uint8_t *d_d1, const uint8_t *d_d2, const uint8_t *d_s1,

@@ -14,8 +14,6 @@
 //     anything else throws std::invalid_argument (the reference would throw cv_bridge::Exception for encodings
 //     it can not convert, src/disparity_to_point_cloud.cpp:50).
 //   * the nine printf progress lines per frame (cpp:47-91) are dropped; `verbose` prints "Cloud size: N".
-//   * MatchingScoreCb{1,2} cache the score image as received: the Gaussian/Sobel preprocessing chain
-//     (src/depth_map_fusion.cpp:70-76, 89-95) is outside this round's scope.
 //   * the six debug publishers of the fusion node (colourised views) are not produced.
 #pragma once
 #include <algorithm>
@@ -231,10 +229,24 @@ class DepthMapFusion {
   d2pc_b200::Bus &nh_;
   std::string fused_topic_;
   d2pc_ctx *ctx_ = nullptr;
-  // the reference caches cropped cv::Mat views (depth_map_fusion.hpp:79-85); the crop and the rotation are index
-  // arithmetic inside the fusion kernel, so the full frames are cached instead
-  sensor_msgs::Image depth_1_, depth_2_, score_1_, score_2_;
+  // the reference caches cropped cv::Mat views (depth_map_fusion.hpp:79-85).  For the depth maps the crop and the
+  // rotation are index arithmetic inside the fusion kernel, so the full frames are cached; the scores are cached
+  // as the n x n preprocessed images, exactly what cropped_score_{1,2}_ (== cropped_score_{1,2}_grad_) hold.
+  sensor_msgs::Image depth_1_, depth_2_;
+  std::vector<uint8_t> cropped_score_1_, cropped_score_2_;
+  uint32_t score_n_1_ = 0, score_n_2_ = 0;
   bool have_d1_ = false, have_d2_ = false, have_s1_ = false, have_s2_ = false;
+
+  // src/depth_map_fusion.cpp:64-80 / :82-99 on the GPU (d2pc_preprocess_score)
+  void preprocess(const sensor_msgs::ImageConstPtr &msg, int which, std::vector<uint8_t> &slot, uint32_t &n, bool &have) {
+    d2pc_b200::require_mono8(*msg);
+    d2pc_image out;
+    d2pc_b200::check(d2pc_preprocess_score(ctx_, msg->data.data(), msg->width, msg->height, msg->step, which, &out),
+                     "d2pc_preprocess_score", ctx_);
+    n = out.width;
+    slot.assign(out.data, out.data + static_cast<size_t>(out.step) * out.height);
+    have = true;
+  }
 
   void cache(const sensor_msgs::ImageConstPtr &msg, sensor_msgs::Image &slot, bool &have) {
     d2pc_b200::require_mono8(*msg);
@@ -273,34 +285,39 @@ class DepthMapFusion {
     cache(msg, depth_2_, have_d2_);
     publishFusedDepthMap(msg);
   }
-  void MatchingScoreCb1(const sensor_msgs::ImageConstPtr &msg) { cache(msg, score_1_, have_s1_); }  // cpp:64-80
-  void MatchingScoreCb2(const sensor_msgs::ImageConstPtr &msg) { cache(msg, score_2_, have_s2_); }  // cpp:82-99
+  void MatchingScoreCb1(const sensor_msgs::ImageConstPtr &msg) {  // cpp:64-80
+    preprocess(msg, 1, cropped_score_1_, score_n_1_, have_s1_);
+  }
+  void MatchingScoreCb2(const sensor_msgs::ImageConstPtr &msg) {  // cpp:82-99
+    preprocess(msg, 2, cropped_score_2_, score_n_2_, have_s2_);
+  }
 
   // src/depth_map_fusion.cpp:103-136
   void publishFusedDepthMap(const sensor_msgs::ImageConstPtr &msg) {
     if (!have_d1_ || !have_d2_ || !have_s1_ || !have_s2_) return;  // :108-111
     const uint32_t w = depth_2_.width, h = depth_2_.height;
-    for (const sensor_msgs::Image *m : {&depth_1_, &score_1_, &score_2_})
-      if (m->width != w || m->height != h) throw std::invalid_argument("fusion inputs differ in size");
-    // d2pc_fuse wants one common step: repack any frame whose step differs
+    if (depth_1_.width != w || depth_1_.height != h) throw std::invalid_argument("fusion inputs differ in size");
+    int r1[4], r2[4], rc[4], dims[3];
+    d2pc_b200::check(d2pc_fuse_geometry(ctx_, w, h, r1, r2, rc, dims), "d2pc_fuse_geometry");
+    if (score_n_1_ != static_cast<uint32_t>(dims[0]) || score_n_2_ != static_cast<uint32_t>(dims[0]))
+      throw std::invalid_argument("cached scores do not match the depth maps' crop");
+    // d2pc_fuse_preprocessed wants one common step for the two depth frames: repack if they differ
     auto dense = [&](const sensor_msgs::Image &m, std::vector<uint8_t> &tmp) -> const uint8_t * {
       if (m.step == w) return m.data.data();
       tmp.resize(static_cast<size_t>(w) * h);
       for (uint32_t y = 0; y < h; ++y) std::copy_n(m.data.data() + static_cast<size_t>(y) * m.step, w, tmp.data() + static_cast<size_t>(y) * w);
       return tmp.data();
     };
-    std::vector<uint8_t> t1, t2, t3, t4;
+    std::vector<uint8_t> t1, t2;
     d2pc_image fused, combined;
-    d2pc_b200::check(d2pc_fuse(ctx_, dense(depth_1_, t1), dense(depth_2_, t2), dense(score_1_, t3),
-                               dense(score_2_, t4), w, h, w, &fused, &combined),
-                     "d2pc_fuse", ctx_);
+    d2pc_b200::check(d2pc_fuse_preprocessed(ctx_, dense(depth_1_, t1), dense(depth_2_, t2), cropped_score_1_.data(),
+                                            cropped_score_2_.data(), w, h, w, &fused, &combined),
+                     "d2pc_fuse_preprocessed", ctx_);
     // :113, :118-121: cropped_score_combined_ aliases cropped_score_1_, so after a fusion pass the cached score 1
-    // holds min(score1, score2) over the merged square until the next MatchingScoreCb1 replaces it.
-    int r1[4], r2[4], rc[4], dims[3];
-    d2pc_b200::check(d2pc_fuse_geometry(ctx_, w, h, r1, r2, rc, dims), "d2pc_fuse_geometry");
+    // holds min(score1, score2) until the next MatchingScoreCb1 replaces it.
     for (int i = 0; i < dims[0]; ++i)
       std::copy_n(combined.data + static_cast<size_t>(i) * combined.step, dims[0],
-                  score_1_.data.data() + static_cast<size_t>(r1[1] + i) * score_1_.step + r1[0]);
+                  cropped_score_1_.data() + static_cast<size_t>(i) * dims[0]);
     auto out = std::make_shared<sensor_msgs::Image>();  // disparity->toImageMsg(fused_image), :134-135
     out->header = msg->header;
     out->height = fused.height;

@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
         L.d2pc_oracle_fuse.argtypes = [_u8p, _u8p, _u8p, _u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
                                        C.c_int, _u8p, _u8p, _i32p]
         L.d2pc_oracle_fuse.restype = C.c_int
+        L.d2pc_oracle_score_preprocess.argtypes = [_u8p, C.c_int, C.c_int, C.c_size_t, _i32p, C.c_int, _u8p]
+        L.d2pc_oracle_score_preprocess.restype = C.c_int
         L.d2pc_oracle_run_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, _f64p,
                                              _u8p, C.c_size_t, C.c_int]
         L.d2pc_oracle_run_frames.restype = C.c_size_t
@@ -217,6 +219,18 @@ def fuse(d1, d2, s1, s2, offset_x=-7, offset_y=15, mode=0):
         raise ValueError("fusion geometry leaves the image")
     n, ow, oh = (int(v) for v in dims)
     return fused[: ow * oh].reshape(oh, ow).copy(), combined[: n * n].reshape(n, n).copy()
+
+
+def score_preprocess(frame: np.ndarray, rect, vertical: bool) -> np.ndarray:
+    """MatchingScoreCb{1,2} on a (rotated, for 2) score frame and its cropToSquare rect (x, y, n, n)."""
+    frame = np.ascontiguousarray(frame, dtype=np.uint8)
+    h, w = frame.shape
+    r = np.array(rect, dtype=np.int32)
+    out = np.empty((int(r[2]), int(r[2])), dtype=np.uint8)
+    rc = lib().d2pc_oracle_score_preprocess(_p(frame, _u8p), w, h, w, _p(r, _i32p), 1 if vertical else 0, _p(out, _u8p))
+    if rc != 0:
+        raise ValueError("bad rectangle")
+    return out
 
 
 def run_frames(frames: np.ndarray, q, mono8: bool, n_threads: int = 1, cloud: np.ndarray | None = None):

@@ -448,6 +448,117 @@ int d2pc_oracle_fuse(const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
 }
 
 /* ------------------------------------------------------------------------- */
+/* matching-score preprocessing (depth_map_fusion.cpp:64-99)                  */
+/* ------------------------------------------------------------------------- */
+
+static inline int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+  return i;
+}
+
+/* cv::GaussianBlur on CV_8U takes OpenCV's bit-exact fixed-point path: the kernel is quantised to 8 fractional
+ * bits with the rounding error diffused so it sums to 256; rows are filtered into 8.8, columns into 16.16, then
+ * rounded half up.  The two kernels the reference uses (13/sigma 3, 21/sigma 10), as OpenCV 4.13 quantises them: */
+static const int kGauss13[13] = {5, 8, 15, 21, 28, 33, 36, 33, 28, 21, 15, 8, 5};
+static const int kGauss21[21] = {9, 9, 11, 11, 12, 13, 13, 14, 14, 15, 14, 15, 14, 14, 13, 13, 12, 11, 11, 9, 9};
+
+/* Blurs the rectangle (x0, y0, ow, oh) of src (sw x sh); border reflect-101 at the edge of src. */
+static void gauss_fixed(const uint8_t *src, int sw, int sh, size_t step, const int *k, int ks, int x0, int y0, int ow,
+                        int oh, uint8_t *dst) {
+  const int r = ks / 2;
+  uint32_t *rows = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(oh + 2 * r) * ow);
+  for (int yy = 0; yy < oh + 2 * r; ++yy) {
+    const uint8_t *s = src + (size_t)reflect101(y0 + yy - r, sh) * step;
+    for (int x = 0; x < ow; ++x) {
+      uint32_t acc = 0;
+      for (int i = 0; i < ks; ++i) acc += (uint32_t)k[i] * s[reflect101(x0 + x + i - r, sw)];
+      rows[(size_t)yy * ow + x] = acc; /* 8.8 */
+    }
+  }
+  for (int y = 0; y < oh; ++y)
+    for (int x = 0; x < ow; ++x) {
+      uint32_t acc = 0;
+      for (int i = 0; i < ks; ++i) acc += (uint32_t)k[i] * rows[(size_t)(y + i) * ow + x];
+      const uint32_t v = (acc + 32768u) >> 16;
+      dst[(size_t)y * ow + x] = (uint8_t)(v > 255 ? 255 : v);
+    }
+  free(rows);
+}
+
+/* cv::Sobel(src, dst, -1, dx, dy, 7, 0.03) on an n x n CV_8U image, (dx,dy) = (0,2) or (2,0): separable float32
+ * filter, kernels getDerivKernels(7): smoothing {1,6,15,20,15,6,1}, 2nd derivative {1,2,-1,-4,-1,2,1}; the
+ * smoothing kernel is the one scaled (in float32).  The pass with the scaled kernel rounds at every step; OpenCV's
+ * AVX2 code uses FMA in its vector loop and mul+add in the scalar tail: the row pass vectorises 32 columns, the
+ * symmetric column pass 4 columns.  The other pass works on integers < 2^24 and is exact. */
+static void sobel7_second(const uint8_t *src, int n, int vertical, uint8_t *dst) {
+  static const float smooth[7] = {1, 6, 15, 20, 15, 6, 1}, deriv[7] = {1, 2, -1, -4, -1, 2, 1};
+  float ks[7];
+  for (int i = 0; i < 7; ++i) ks[i] = smooth[i] * 0.03f;
+  float *t = (float *)malloc(sizeof(float) * (size_t)n * n);
+  if (!vertical) {
+    /* dx = 0, dy = 2: rows = scaled smoothing (sequential k = 0..6), columns = integer derivative */
+    const int vec_end = n - n % 32;
+    for (int y = 0; y < n; ++y)
+      for (int x = 0; x < n; ++x) {
+        float s = ks[0] * (float)src[(size_t)y * n + reflect101(x - 3, n)];
+        for (int i = 1; i < 7; ++i) {
+          const float v = (float)src[(size_t)y * n + reflect101(x + i - 3, n)];
+          s = x < vec_end ? fmaf(ks[i], v, s) : s + ks[i] * v;
+        }
+        t[(size_t)y * n + x] = s;
+      }
+    for (int y = 0; y < n; ++y)
+      for (int x = 0; x < n; ++x) {
+        float s = deriv[3] * t[(size_t)y * n + x];
+        for (int i = 1; i <= 3; ++i)
+          s += deriv[3 + i] * (t[(size_t)reflect101(y + i, n) * n + x] + t[(size_t)reflect101(y - i, n) * n + x]);
+        const float r = rintf(s);
+        dst[(size_t)y * n + x] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+      }
+  } else {
+    /* dx = 2, dy = 0: rows = integer derivative (exact), columns = scaled smoothing, symmetric form */
+    const int vec_end = n - n % 4;
+    for (int y = 0; y < n; ++y)
+      for (int x = 0; x < n; ++x) {
+        float s = 0.f;
+        for (int i = 0; i < 7; ++i) s += deriv[i] * (float)src[(size_t)y * n + reflect101(x + i - 3, n)];
+        t[(size_t)y * n + x] = s;
+      }
+    for (int y = 0; y < n; ++y)
+      for (int x = 0; x < n; ++x) {
+        float s = ks[3] * t[(size_t)y * n + x];
+        for (int i = 1; i <= 3; ++i) {
+          const float v = t[(size_t)reflect101(y + i, n) * n + x] + t[(size_t)reflect101(y - i, n) * n + x];
+          s = x < vec_end ? fmaf(ks[3 + i], v, s) : s + ks[3 + i] * v;
+        }
+        const float r = rintf(s);
+        dst[(size_t)y * n + x] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+      }
+  }
+  free(t);
+}
+
+int d2pc_oracle_score_preprocess(const uint8_t *frame, int w, int h, size_t step, const int rect[4], int vertical,
+                                 uint8_t *out) {
+  const int x0 = rect[0], y0 = rect[1], n = rect[2];
+  if (n <= 0 || rect[3] != n || x0 < 0 || y0 < 0 || x0 + n > w || y0 + n > h) return -1;
+  uint8_t *g = (uint8_t *)malloc((size_t)n * n), *e = (uint8_t *)malloc((size_t)n * n);
+  gauss_fixed(frame, w, h, step, kGauss13, 13, x0, y0, n, n, g);            /* :70-71 / :89-90 */
+  sobel7_second(g, n, vertical, e);                                            /* :72 / :91 */
+  for (size_t i = 0; i < (size_t)n * n; ++i) e[i] = e[i] > 30 ? 255 : 0;       /* :73 / :92 THRESH_BINARY */
+  gauss_fixed(e, n, n, (size_t)n, kGauss21, 21, 0, 0, n, n, g);              /* :74-75 / :93-94 */
+  for (int y = 0; y < n; ++y)                                                  /* :76 / :95 saturating s + 2g */
+    for (int x = 0; x < n; ++x) {
+      const int v = frame[(size_t)(y0 + y) * step + x0 + x] + 2 * g[(size_t)y * n + x];
+      out[(size_t)y * n + x] = (uint8_t)(v > 255 ? 255 : v);
+    }
+  free(e);
+  free(g);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* CPU baseline driver                                                        */
 /* ------------------------------------------------------------------------- */
 

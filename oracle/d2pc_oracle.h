@@ -129,6 +129,16 @@ int d2pc_oracle_fuse(const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
                      int offset_x, int offset_y, int mode, uint8_t *fused,
                      uint8_t *combined, int dims[3]);
 
+/* src/depth_map_fusion.cpp:64-80 (vertical = 0, MatchingScoreCb1) / :82-99 (vertical = 1, MatchingScoreCb2):
+ * what the node caches as cropped_score_k_ (== cropped_score_k_grad_) for a score frame (already rotated for
+ * callback 2) and its cropToSquare rectangle rect = {x, y, n, n}:
+ *   GaussianBlur 13x13 sigma 3 (the crop is a non-isolated ROI: the blur sees the frame around it) ->
+ *   Sobel 2nd derivative ksize 7 scale 0.03 -> threshold 30 -> GaussianBlur 21x21 sigma 10 -> score + 2*grad.
+ * Arithmetic pinned against cv2 4.13.0 (AVX2 dispatch): 8.8 fixed-point Gaussian kernels, float32 Sobel whose
+ * scaled pass uses FMA except in the SIMD tail columns.  out is n x n dense.  Returns 0, -1 on bad geometry. */
+int d2pc_oracle_score_preprocess(const uint8_t *frame, int w, int h, size_t step, const int rect[4], int vertical,
+                                 uint8_t *out);
+
 /* ---- CPU baseline helpers (bench.py cpu_baseline / --impl reference) ---- */
 
 /* Runs d2pc_oracle_disparity_cb_f32 (mono8 == 0) or _mono8 (mono8 != 0) over

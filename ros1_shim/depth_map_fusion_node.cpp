@@ -2,13 +2,15 @@
 // Built only where catkin/roscpp exist; NOT built in the development image.
 // Subscriptions, the /fused_depth_map publisher, the offset_x / offset_y parameters follow
 // include/disparity_to_point_cloud/depth_map_fusion.hpp:97-124, so launch/depth_map_fusion.launch works unchanged.
-// The score images are cached as received (the Gaussian/Sobel preprocessing of
-// src/depth_map_fusion.cpp:70-76, 89-95 is not part of this round) and the debug views are not published.
+// Score frames are preprocessed on the GPU as they arrive (Gaussian / Sobel / threshold / Gaussian chain of
+// src/depth_map_fusion.cpp:64-99) and cached as the n x n images the reference caches; debug views are not
+// published.
 #include <ros/ros.h>
 #include <sensor_msgs/Image.h>
 #include <sensor_msgs/image_encodings.h>
 
 #include <cstring>
+#include <vector>
 
 #include "d2pc_b200.h"
 
@@ -35,20 +37,26 @@ class DepthMapFusionGpu {
   ~DepthMapFusionGpu() { d2pc_destroy(ctx_); }
 
   void DisparityCb1(const sensor_msgs::ImageConstPtr &m) { d1_ = m; }
-  void MatchingScoreCb1(const sensor_msgs::ImageConstPtr &m) { s1_ = m; }
-  void MatchingScoreCb2(const sensor_msgs::ImageConstPtr &m) { s2_ = m; }
+  void MatchingScoreCb1(const sensor_msgs::ImageConstPtr &m) { Preprocess(m, 1, s1_); }
+  void MatchingScoreCb2(const sensor_msgs::ImageConstPtr &m) { Preprocess(m, 2, s2_); }
+  void Preprocess(const sensor_msgs::ImageConstPtr &m, int which, std::vector<uint8_t> &slot) {
+    d2pc_image out;
+    if (d2pc_preprocess_score(ctx_, m->data.data(), m->width, m->height, m->step, which, &out) != D2PC_OK) return;
+    slot.assign(out.data, out.data + static_cast<size_t>(out.step) * out.height);
+  }
   void DisparityCb2(const sensor_msgs::ImageConstPtr &m) {
     d2_ = m;
-    if (!d1_ || !s1_ || !s2_) return;  // have not received all maps and scores yet
-    for (const auto &im : {d1_, s1_, s2_})
-      if (im->width != m->width || im->height != m->height || im->step != m->step) return;
+    if (!d1_ || s1_.empty() || s2_.empty()) return;  // have not received all maps and scores yet
+    if (d1_->width != m->width || d1_->height != m->height || d1_->step != m->step) return;
     d2pc_image fused, combined;
-    const int rc = d2pc_fuse(ctx_, d1_->data.data(), d2_->data.data(), s1_->data.data(), s2_->data.data(), m->width,
-                             m->height, m->step, &fused, &combined);
+    const int rc = d2pc_fuse_preprocessed(ctx_, d1_->data.data(), d2_->data.data(), s1_.data(), s2_.data(), m->width,
+                                          m->height, m->step, &fused, &combined);
     if (rc != D2PC_OK) {
-      ROS_ERROR("d2pc_fuse: %s", d2pc_strerror(rc));
+      ROS_ERROR("d2pc_fuse_preprocessed: %s", d2pc_strerror(rc));
       return;
     }
+    // the reference's combined score aliases its cached score 1 (src/depth_map_fusion.cpp:113)
+    s1_.assign(combined.data, combined.data + static_cast<size_t>(combined.step) * combined.height);
     sensor_msgs::Image out;
     out.header = m->header;
     out.height = fused.height;
@@ -67,7 +75,8 @@ class DepthMapFusionGpu {
   ros::NodeHandle nh_;
   ros::Subscriber d1_sub_, d2_sub_, s1_sub_, s2_sub_;
   ros::Publisher fused_pub_;
-  sensor_msgs::ImageConstPtr d1_, d2_, s1_, s2_;
+  sensor_msgs::ImageConstPtr d1_, d2_;
+  std::vector<uint8_t> s1_, s2_;
   d2pc_ctx *ctx_ = nullptr;
 };
 

@@ -125,6 +125,20 @@ def score_preprocess_cv(score, vertical):
     return cv2.add(score, cv2.add(g, g))  # score + 2*grad, saturating u8 MatExpr
 
 
+def score_chain(frame, x, y, n, vertical):
+    """MatchingScoreCb1 (vertical=False, src/depth_map_fusion.cpp:64-80) / Cb2 (True, :82-99) for a score frame
+    (already rotated for Cb2) and its cropToSquare rectangle."""
+    score = frame[y:y + n, x:x + n].copy()
+    g = cv2.GaussianBlur(frame, (13, 13), 3.0)[y:y + n, x:x + n].copy()
+    if vertical:
+        g = cv2.Sobel(g, -1, 2, 0, ksize=7, scale=0.03)
+    else:
+        g = cv2.Sobel(g, -1, 0, 2, ksize=7, scale=0.03)
+    _, g = cv2.threshold(g, 30, 255, 0)
+    g = cv2.GaussianBlur(g, (21, 21), 10.0)
+    return cv2.add(score, cv2.add(g, g))
+
+
 def main():
     rng = np.random.default_rng(20261018)
     assert cv2.__version__.startswith("4."), cv2.__version__
@@ -204,6 +218,28 @@ def main():
         sp[f"sob_h{i}"] = cv2.Sobel(sp[f"g13_{i}"], -1, 0, 2, ksize=7, scale=0.03)
         sp[f"sob_v{i}"] = cv2.Sobel(sp[f"g13_{i}"], -1, 2, 0, ksize=7, scale=0.03)
     np.savez_compressed(os.path.join(HERE, "score_golden.npz"), **sp)
+    # ---- the whole MatchingScoreCb chain on full frames, ROI semantics included ------------------------------
+    # cropped_score_k_ is a non-isolated ROI of the (rotated) frame, so the first GaussianBlur sees the pixels
+    # around the ROI: equivalent to blurring the whole frame and cropping.  Everything after that runs on a
+    # stand-alone n x n Mat (reflect-101 at its own edge).
+    ch = {}
+    for i, (h, w, ox, oy) in enumerate([(150, 200, -7, 15), (160, 120, 5, -9), (300, 424, -7, 15)]):
+        s1 = cv2.GaussianBlur(rng.integers(0, 256, size=(h, w), dtype=np.uint8), (7, 7), 2.0)
+        s2 = cv2.GaussianBlur(rng.integers(0, 256, size=(h, w), dtype=np.uint8), (7, 7), 2.0)
+        for a in (s1, s2):
+            for _ in range(6):
+                y, x = int(rng.integers(0, h - 4)), int(rng.integers(0, w - 4))
+                a[y:y + 3, :] = int(rng.integers(0, 256))
+                a[:, x:x + 2] = int(rng.integers(0, 256))
+        x1, y1, n = crop_to_square(w, h, ox, oy, oy)
+        x2, y2, n2 = crop_to_square(h, w, -ox, -oy, oy)
+        pre1 = score_chain(s1, x1, y1, n, vertical=False)
+        pre2 = score_chain(rotate_cw(s2), x2, y2, n, vertical=True)
+        if i == 2:  # keep the big case small on disk: store the inputs' seed-free digest rows only
+            ch.update({f"s1_{i}": s1, f"s2_{i}": s2, f"off_{i}": np.array([ox, oy]), f"pre1_{i}": pre1, f"pre2_{i}": pre2})
+        else:
+            ch.update({f"s1_{i}": s1, f"s2_{i}": s2, f"off_{i}": np.array([ox, oy]), f"pre1_{i}": pre1, f"pre2_{i}": pre2})
+    np.savez_compressed(os.path.join(HERE, "score_chain_golden.npz"), **ch)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -72,7 +72,16 @@ def test_fusion_node_then_node1_config5(harness, tmp_path):
     fused_bin, cloud_bin = tmp_path / "fused.bin", tmp_path / "cloud.bin"
     subprocess.run([harness, "fusion", os.path.join(ROOT, "launch", "depth_map_fusion.launch"), str(w), str(h)] + paths +
                    [str(fused_bin), str(cloud_bin)], check=True)
-    fused, _ = oracle.fuse(d1, d2, s1, s2, -7, 15)
+    # MatchingScoreCb1/2 preprocess the scores (src/depth_map_fusion.cpp:64-99) before they are cached
+    _, r1 = oracle.crop_to_square(w, h, -7, 15, 15)
+    _, r2 = oracle.crop_to_square(h, w, 7, -15, 15)
+    p1 = oracle.score_preprocess(s1, r1, False)
+    p2 = oracle.score_preprocess(oracle.rotate_cw(s2), r2, True)
+    c1 = np.zeros((h, w), np.uint8)
+    c1[r1[1]:r1[1] + r1[2], r1[0]:r1[0] + r1[2]] = p1
+    rot = np.zeros((w, h), np.uint8)
+    rot[r2[1]:r2[1] + r2[2], r2[0]:r2[0] + r2[2]] = p2
+    fused, _ = oracle.fuse(d1, d2, c1, np.ascontiguousarray(np.rot90(rot, 1)), -7, 15)
     assert fused.shape == (665, 665)
     assert fused_bin.read_bytes() == image_msg(fused, 2, 500)          # header of message 2 (:134-135)
     want = oracle.serialize_pointcloud2(oracle.disparity_cb_mono8(fused, q), seq=0, sec=2, nsec=500)

@@ -145,3 +145,15 @@ def test_pointcloud2_wire_layout():
         want += struct.pack("<I", 1) + nm + struct.pack("<IBI", 4 * i, 7, 1)
     want += struct.pack("<BIII", 0, 16, 32, 32) + pts.tobytes() + b"\x00"
     assert msg == want
+
+
+def test_score_preprocess_chain_cv2():
+    g = golden("score_chain_golden.npz")
+    for i in range(3):
+        s1, s2 = g[f"s1_{i}"], g[f"s2_{i}"]
+        ox, oy = (int(v) for v in g[f"off_{i}"])
+        h, w = s1.shape
+        _, r1 = oracle.crop_to_square(w, h, ox, oy, oy)
+        _, r2 = oracle.crop_to_square(h, w, -ox, -oy, oy)
+        assert_same_bits(oracle.score_preprocess(s1, r1, False), g[f"pre1_{i}"], f"MatchingScoreCb1 #{i}")
+        assert_same_bits(oracle.score_preprocess(oracle.rotate_cw(s2), r2, True), g[f"pre2_{i}"], f"MatchingScoreCb2 #{i}")
