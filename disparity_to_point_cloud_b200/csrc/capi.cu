@@ -78,7 +78,7 @@ struct d2pc_ctx {
   // tuning / test hooks
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0;
   bool force_scalar = false, force_generic = false;
-  int compact_variant = 0;
+  int compact_variant = 0, exact_variant = 0;
 };
 
 namespace {
@@ -231,6 +231,7 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
   L.force_scalar = ctx->force_scalar;
   L.force_generic = ctx->force_generic;
   L.compact_variant = ctx->compact_variant;
+  L.exact_variant = ctx->exact_variant;
   CU(ctx, launch_reproject(L, stream, &nl));
   ctx->launches += nl;
   return D2PC_OK;
@@ -450,6 +451,7 @@ int d2pc_create(const d2pc_config *cfg, int device, d2pc_ctx **out) {
   if (const char *v = getenv("D2PC_ROWS_PER_UNIT")) ctx->rows_per_unit = atoi(v);
   if (const char *v = getenv("D2PC_CTAS_PER_SM")) ctx->ctas_per_sm = atoi(v);
   if (const char *v = getenv("D2PC_MEDIAN_STRIP")) ctx->median_strip = atoi(v);
+  if (const char *v = getenv("D2PC_EXACT_VARIANT")) ctx->exact_variant = atoi(v);
 
   // pre-size the slots when the caller told us the largest frame
   if (c.max_width > 0 && c.max_height > 0) {
@@ -524,6 +526,7 @@ int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value) {
   else if (k == "force_scalar") ctx->force_scalar = value != 0;
   else if (k == "force_generic") ctx->force_generic = value != 0;
   else if (k == "force_park" || k == "compact_variant") ctx->compact_variant = value;
+  else if (k == "exact_variant") ctx->exact_variant = value;
   else if (k == "median_ksize") {
     if (value < 1 || value > 15 || !(value & 1)) return D2PC_ERR_INVALID_ARG;
     ctx->cfg.median_ksize = value;

@@ -55,8 +55,8 @@ struct ReprojArgs {
   QParams Q;
 };
 
-enum { kMathRect0 = 0, kMathRectW = 1, kMathGeneric = 2, kMathFast = 3 };
-#define D2PC_IS_RECT(m) ((m) == kMathRect0 || (m) == kMathRectW)
+enum { kMathRect0 = 0, kMathRectW = 1, kMathGeneric = 2, kMathFast = 3, kMathRect0M = 4 };  // M: Markstein quotients
+#define D2PC_IS_RECT(m) ((m) == kMathRect0 || (m) == kMathRectW || (m) == kMathRect0M)
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
   float4 v;
@@ -111,8 +111,8 @@ __device__ __forceinline__ void points_of4(const QParams &Q, const double (&xd)[
     bool slow[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      p[k] = reproject_exact_rectified<kMath == kMathRect0>(Q, xd[k], yd, yslow || ((xslow >> k) & 1u), d[k],
-                                                            slow[k]);
+      p[k] = reproject_exact_rectified<kMath != kMathRectW, kMath == kMathRect0>(
+          Q, xd[k], yd, yslow || ((xslow >> k) & 1u), d[k], slow[k]);
     if (__builtin_expect(slow[0] || slow[1] || slow[2] || slow[3], 0)) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -132,7 +132,7 @@ __device__ __forceinline__ float4 point_of(const QParams &Q, int u, int v, float
   if constexpr (D2PC_IS_RECT(kMath)) {
     const double xd = rect_axis_const(u, Q.q03), yd = rect_axis_const(v, Q.q13);
     bool slow;
-    float4 p = reproject_exact_rectified<kMath == kMathRect0>(
+    float4 p = reproject_exact_rectified<kMath != kMathRectW, kMath == kMathRect0>(
         Q, xd, yd, rect_axis_slow(xd) || rect_axis_slow(yd) || Q.zd_slow, d, slow);
     if (__builtin_expect(slow, 0)) p = reproject_exact_slow(Q.q, u, v, d);
     return p;
@@ -915,12 +915,18 @@ void make_qparams(const double q[16], QParams *out) {
   P.q32 = q[14];
   P.q33 = q[15];
   P.q33_zero = (q[15] == 0.0) ? 1 : 0;
+  {
+    float dhi = (float)(0x1p64 / (a32 > 0 ? a32 : 1.0));
+    if (!(dhi < 3.0e38f)) dhi = 3.0e38f;
+    if (dhi < 0x1p-125f) dhi = 0x1p-125f;
+    memcpy(&P.dhi_bits, &dhi, 4);
+  }
   // h2 = ((0*u + 0*v) + 0*d) + q23 = (+0) + q23 for finite u, v >= 0 and finite d
   volatile double z = 0.0;
   const double h2 = z + q[11];
   P.zd = (double)(float)h2;
   const uint64_t zb = bits(P.zd);
-  P.zd_slow = ((zb << 1) == 0 || ((zb >> 52) & 0x7ff) == 0x7ff) ? 1 : 0;
+  P.zd_slow = (((zb >> 52) & 0x7ff) == 0x7ff || ((zb >> 52) & 0x7ff) < 1023 - 40) ? 1 : 0;  // as rect_axis_slow
   {
     uint32_t zi = (zb << 1) == 0 ? 0xFFC00000u : (uint32_t)(((zb >> 63) << 31) | 0x7f800000u);
     memcpy(&P.zinf, &zi, 4);
@@ -979,7 +985,9 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
                    (cw % 4 == 0 || L.border >= 3) && !L.force_scalar;
 
   const int math = L.arith_fast ? kMathFast
-                   : (a.Q.rectified && !L.force_generic ? (a.Q.q33_zero ? kMathRect0 : kMathRectW) : kMathGeneric);
+                   : (a.Q.rectified && !L.force_generic
+                          ? (a.Q.q33_zero ? (L.exact_variant == 1 ? kMathRect0M : kMathRect0) : kMathRectW)
+                          : kMathGeneric);
   const bool compact = L.compact;
 
   int grid;
@@ -1062,12 +1070,13 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
     a.total_units = (uint32_t)total;
     grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
   }
-  const int min_blocks = L.ctas_per_sm > 0 ? L.ctas_per_sm : 8;
+  const int min_blocks = L.ctas_per_sm > 0 ? L.ctas_per_sm : 7;
   if (launches) *launches += 1;
 
 #define D2PC_DISPATCH(T)                                                          \
   switch (math) {                                                                 \
     case kMathRect0: return launch_typed<T, kMathRect0>(a, vec, compact, grid, min_blocks, stream); \
+    case kMathRect0M: return launch_typed<T, kMathRect0M>(a, vec, compact, grid, min_blocks, stream); \
     case kMathRectW: return launch_typed<T, kMathRectW>(a, vec, compact, grid, min_blocks, stream); \
     case kMathGeneric: return launch_typed<T, kMathGeneric>(a, vec, compact, grid, min_blocks, stream); \
     default: return launch_typed<T, kMathFast>(a, vec, compact, grid, min_blocks, stream);    \

@@ -15,6 +15,7 @@ struct QParams {
   double zd;     // (double)(float)((+0.0) + q23)
   float qf[16];  // float32 copy of Q for FAST mode
   float zinf;    // zd / (+0): +-inf, or the x86 NaN when zd == 0
+  uint32_t dhi_bits;  // float bits of 2^64 / |q32|: larger disparities leave the straight-line path
   int rectified;
   int q33_zero;
   int zd_slow;   // zd is +-0 / inf / NaN: the straight-line path must not be used
@@ -44,6 +45,7 @@ struct ReprojectLaunch {
   int ctas_per_sm = 0;
   bool force_scalar = false;   // exercise the unaligned load path
   bool force_generic = false;  // exercise the generic-Q exact path on a rectified Q
+  int exact_variant = 0;       // rectified exact quotients: 0 = guarded multiply (7 FP64 ops), 1 = Markstein (15)
   int compact_variant = 0;     // CROP_FINITE kernel: 0 = automatic (band), 1 = park-then-compact, 2 = classify-first
 };
 

@@ -142,7 +142,7 @@ def test_golden_fixture_cv2(ctx):
     ctx.set_q(_default_q())
 
 
-@pytest.mark.parametrize("knob", ["force_scalar", "force_generic"])
+@pytest.mark.parametrize("knob", ["force_scalar", "force_generic", "exact_variant"])
 def test_alternate_code_paths_agree(ctx, knob):
     ctx.set_q(_default_q())
     d = synth.s4_stress(300, 1000, 6)
@@ -152,6 +152,29 @@ def test_alternate_code_paths_agree(ctx, knob):
         assert_same_bits(ctx.process_f32(d), want, knob)
     finally:
         ctx.set_tuning(knob, 0)
+
+
+def test_markstein_variant_special_values_and_4k(ctx):
+    """exact_variant 1 (Markstein quotients) against the oracle on the inputs that stress the guards."""
+    ctx.set_q(_default_q())
+    ctx.set_tuning("exact_variant", 1)
+    try:
+        d = synth.s4_stress(120, 3840, 11)
+        flat = d.reshape(-1)
+        for i, v in enumerate([np.inf, -np.inf, np.nan, -0.0, 1e-42, -3.5, 3e38, 1e-38, 2e19, 1e25]):
+            flat[i::31] = np.float32(v)
+        assert_same_bits(ctx.process_f32(d), oracle.disparity_cb_f32(d, _default_q()), "markstein")
+    finally:
+        ctx.set_tuning("exact_variant", 0)
+
+
+def test_guarded_multiply_large_and_tiny_disparities(ctx):
+    """default variant: disparities beyond d_hi = 2^64/|q32| and near the float-denormal result range."""
+    ctx.set_q(_default_q())
+    rng = np.random.default_rng(12)
+    d = np.exp(rng.uniform(np.log(1e-38), np.log(3e38), size=(200, 512))).astype(np.float32)
+    d[::3, ::5] *= -1
+    assert_same_bits(ctx.process_f32(d), oracle.disparity_cb_f32(d, _default_q()), "log-uniform disparities")
 
 
 def test_unaligned_and_strided_input(ctx):
