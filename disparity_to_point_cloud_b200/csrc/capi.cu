@@ -76,7 +76,7 @@ struct d2pc_ctx {
   PinBuf h_score[2];
   cudaEvent_t ev_fuse = nullptr;
   // tuning / test hooks
-  int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0;
+  int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0, median_variant = 0;
   bool force_scalar = false, force_generic = false;
   int compact_variant = 0, exact_variant = 0;
 };
@@ -201,6 +201,7 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
     M.ksize = c.median_ksize;
     M.sm_count = ctx->sm_count;
     M.strip_rows = ctx->median_strip;
+    M.variant = ctx->median_variant;
     CU(ctx, launch_median_u8(M, stream, &nl));
     ctx->launches += nl;
     reproj_in = d_med;
@@ -523,6 +524,7 @@ int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value) {
   if (k == "rows_per_unit") ctx->rows_per_unit = value;
   else if (k == "ctas_per_sm") ctx->ctas_per_sm = value;
   else if (k == "median_strip") ctx->median_strip = value;
+  else if (k == "median_variant") ctx->median_variant = value;
   else if (k == "force_scalar") ctx->force_scalar = value != 0;
   else if (k == "force_generic") ctx->force_generic = value != 0;
   else if (k == "force_park" || k == "compact_variant") ctx->compact_variant = value;
@@ -697,6 +699,7 @@ int d2pc_median_u8_device(d2pc_ctx *ctx, const uint8_t *d_src, uint32_t w, uint3
   M.ksize = ksize;
   M.sm_count = ctx->sm_count;
   M.strip_rows = ctx->median_strip;
+  M.variant = ctx->median_variant;
   int nl = 0;
   CU(ctx, launch_median_u8(M, ctx->s_compute, &nl));
   ctx->launches += nl;
@@ -769,6 +772,7 @@ static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2,
     M.dst = reinterpret_cast<uint8_t *>(reinterpret_cast<uintptr_t>(d_fused) - ((size_t)g.out_y * g.out_w + g.out_x));
     M.ksize = c.fuse_median_ksize;
     M.sm_count = ctx->sm_count;
+    M.variant = ctx->median_variant;
     CU(ctx, launch_median_u8(M, ctx->s_compute, &nl));
     ctx->launches += nl;
   } else {

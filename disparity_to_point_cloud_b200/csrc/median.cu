@@ -36,20 +36,20 @@ struct MedianArgs {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-// byte address of counter (bin, lane) inside a warp's 8 KB histogram
-__device__ __forceinline__ uint32_t hist_addr(uint32_t bin, uint32_t lane) {
-  return (((bin >> 2) * 32u + lane) << 2) | (bin & 3u);
-}
+// Offset of 8-bit counter `bin` inside a lane's private histogram column (add 4*lane for the byte address):
+// monotonic in `bin`, so window pixels are kept in the ring already transformed and compared in this domain.
+__device__ __forceinline__ uint32_t hist_off(uint32_t bin) { return ((bin >> 2) << 7) | (bin & 3u); }
 
 template <int K>
 __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_constant__ MedianArgs a) {
   constexpr int R = K / 2;
   constexpr int kRank = (K * K) / 2;
   __shared__ __align__(16) uint8_t s_hist[kWarps][256 * 32];
-  __shared__ __align__(4) uint8_t s_ring[kWarps][K][kRingPitch];
+  __shared__ __align__(4) uint16_t s_ring[kWarps][K][kRingPitch];  // hist_off() of the K most recent rows
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   uint8_t *hist = s_hist[wic];
-  uint8_t(*ring)[kRingPitch] = s_ring[wic];
+  uint8_t *hb = hist + 4 * lane;  // this lane's column: counter `bin` lives at hb[hist_off(bin)]
+  uint16_t(*ring)[kRingPitch] = s_ring[wic];
 
   for (uint32_t unit = blockIdx.x * kWarps + wic; unit < a.total_units; unit += gridDim.x * kWarps) {
     const uint32_t f = unit / a.units_per_frame;
@@ -73,20 +73,20 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
     for (int i = 0; i < (256 * 32) / (32 * 16); ++i)
       reinterpret_cast<uint4 *>(hist)[i * 32 + lane] = make_uint4(0, 0, 0, 0);
 
-    // ---- fill the ring with window rows of the first output row
+    // ---- fill the ring with the window rows of the first output row
 #pragma unroll
     for (int s = 0; s < K; ++s) {
       const uint8_t *row = src + (size_t)clampi(y_first - R + s, 0, a.height - 1) * a.src_step;
-      ring[s][lane] = row[gx_a];
-      if (lane < K - 1) ring[s][32 + lane] = row[gx_b];
+      ring[s][lane] = (uint16_t)hist_off(row[gx_a]);
+      if (lane < K - 1) ring[s][32 + lane] = (uint16_t)hist_off(row[gx_b]);
     }
     __syncwarp();
 #pragma unroll 1
     for (int s = 0; s < K; ++s) {
 #pragma unroll
       for (int dx = 0; dx < K; ++dx) {
-        const uint32_t ad = hist_addr(ring[s][lane + dx], lane);
-        hist[ad] = hist[ad] + 1;
+        const uint32_t off = ring[s][lane + dx];
+        hb[off] = hb[off] + 1;
       }
     }
     // ---- initial median: walk 4 bins (one word) at a time, then bin by bin
@@ -100,8 +100,152 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
         below += s4;
       }
       med = w * 4;
-      while (below + (int)hist[hist_addr(med, lane)] <= kRank) {
-        below += hist[hist_addr(med, lane)];
+      while (below + (int)hb[hist_off(med)] <= kRank) {
+        below += hb[hist_off(med)];
+        ++med;
+      }
+    }
+    uint32_t med_off = hist_off(med);
+
+    int slot = 0;  // ring slot holding the oldest window row
+    for (int y = y_first; y < y_end; ++y) {
+      if (col_ok) dst[(size_t)y * a.dst_step + x0 + lane] = (uint8_t)med;
+      if (y + 1 >= y_end) break;
+      // prefetch the row entering the window
+      const uint8_t *row = src + (size_t)clampi(y + 1 + R, 0, a.height - 1) * a.src_step;
+      const uint32_t na = hist_off(row[gx_a]);
+      const uint32_t nb = (lane < K - 1) ? hist_off(row[gx_b]) : 0u;
+      // remove the oldest row
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const uint32_t off = ring[slot][lane + dx];
+        hb[off] = hb[off] - 1;
+        below -= (off < med_off) ? 1 : 0;
+      }
+      __syncwarp();
+      ring[slot][lane] = (uint16_t)na;
+      if (lane < K - 1) ring[slot][32 + lane] = (uint16_t)nb;
+      __syncwarp();
+      // add the new row
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const uint32_t off = ring[slot][lane + dx];
+        hb[off] = hb[off] + 1;
+        below += (off < med_off) ? 1 : 0;
+      }
+      slot = (slot + 1 == K) ? 0 : slot + 1;
+      // re-centre: invariant below <= kRank < below + hist[med]
+      while (below > kRank) {
+        --med;
+        below -= hb[hist_off(med)];
+      }
+      for (;;) {
+        const int hm = hb[hist_off(med)];
+        if (below + hm > kRank) break;
+        below += hm;
+        ++med;
+      }
+      med_off = hist_off(med);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Column-histogram variant: the same exact median with two histogram updates per thread and row.
+// ---------------------------------------------------------------------------
+// Every image column of the warp's footprint (32 outputs + 2R halo) keeps the histogram of its K most recent
+// pixels; moving down one row changes each column histogram by one pixel out, one pixel in.  The window histogram
+// of an output is the sum of K adjacent column histograms and is never materialised: the running median needs
+//   below  = #{window pixels < med}: updated from the 2K pixels that left / entered (register compares), and
+//   W(med) = window count of bin med: K shared-memory reads of neighbouring columns (conflict-free layout).
+// The serial read-modify-write chain per row shrinks from 2K to 2 (4 for the lanes that own a halo column), the
+// rest is independent loads + ALU.  Layout: counter (bin, column c) at byte (bin>>2)*256 + c*4 + (bin&3): a warp
+// touching 32 consecutive columns hits 32 distinct banks whatever the bins are.
+constexpr int kColWarps = 4;
+constexpr int kColThreads = kColWarps * 32;
+constexpr int kColHistBytes = 64 * 256;  // 64 bin groups x 64 column slots x 4 counters = 16 KB per warp
+
+__device__ __forceinline__ uint32_t col_off(uint32_t bin) { return ((bin >> 2) << 8) | (bin & 3u); }
+
+template <int K>
+__global__ void __launch_bounds__(kColThreads) median_col_kernel(const __grid_constant__ MedianArgs a) {
+  constexpr int R = K / 2;
+  constexpr int kRank = (K * K) / 2;
+  extern __shared__ __align__(16) uint8_t s_dyn[];  // [kColWarps][kColHistBytes] histograms, then the rings
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  uint8_t *hist = s_dyn + (size_t)wic * kColHistBytes;
+  uint8_t(*ring)[kRingPitch] = reinterpret_cast<uint8_t(*)[kRingPitch]>(s_dyn + (size_t)kColWarps * kColHistBytes +
+                                                                       (size_t)wic * K * kRingPitch);
+  uint8_t *own_a = hist + 4 * lane;         // histogram column of footprint column `lane`
+  uint8_t *own_b = hist + 4 * (32 + lane);  // ... and of halo column 32 + lane (lanes < 2R)
+  const bool has_b = lane < 2 * R;
+
+  for (uint32_t unit = blockIdx.x * kColWarps + wic; unit < a.total_units; unit += gridDim.x * kColWarps) {
+    const uint32_t f = unit / a.units_per_frame;
+    const uint32_t rem = unit - f * a.units_per_frame;
+    const int strip = rem / a.n_colblk;
+    const int cb = rem - strip * a.n_colblk;
+    const int x0 = a.ox0 + cb * 32;
+    const int y_first = a.oy0 + strip * a.strip_rows;
+    const int y_end = min(y_first + a.strip_rows, a.oy0 + a.oh);
+    const uint8_t *src = a.src + (size_t)f * a.src_frame_stride;
+    uint8_t *dst = a.dst + (size_t)f * a.dst_frame_stride;
+    const bool col_ok = (x0 + lane) < (a.ox0 + a.ow);
+    const int gx_a = clampi(x0 - R + lane, 0, a.width - 1);
+    const int gx_b = clampi(x0 - R + 32 + lane, 0, a.width - 1);
+
+    // ---- zero the column histograms, load the first window's rows, build the column histograms
+    __syncwarp();
+#pragma unroll 4
+    for (int i = 0; i < kColHistBytes / (32 * 16); ++i)
+      reinterpret_cast<uint4 *>(hist)[i * 32 + lane] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const uint8_t *row = src + (size_t)clampi(y_first - R + s, 0, a.height - 1) * a.src_step;
+      ring[s][lane] = row[gx_a];
+      if (has_b) ring[s][32 + lane] = row[gx_b];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const uint32_t oa = col_off(ring[s][lane]);
+      own_a[oa] = own_a[oa] + 1;
+      if (has_b) {
+        const uint32_t ob = col_off(ring[s][32 + lane]);
+        own_b[ob] = own_b[ob] + 1;
+      }
+    }
+    __syncwarp();
+    // window count of one bin / of one 4-bin word for this lane's output: columns lane .. lane+K-1
+    auto wcount = [&](int bin) {
+      const uint8_t *p = own_a + col_off((uint32_t)bin);
+      int c = 0;
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) c += p[4 * dx];
+      return c;
+    };
+    // ---- initial median: 4 bins at a time, then bin by bin
+    int med = 0, below = 0;
+    {
+      int g = 0;
+      for (; g < 64; ++g) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(own_a + (g << 8));
+        uint32_t lo = 0, hi = 0;  // byte sums of the K words, two 16-bit lanes each
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+          const uint32_t w = p[dx];
+          lo += w & 0x00ff00ffu;
+          hi += (w >> 8) & 0x00ff00ffu;
+        }
+        const int s4 = (int)((lo & 0xffffu) + (lo >> 16) + (hi & 0xffffu) + (hi >> 16));
+        if (below + s4 > kRank) break;
+        below += s4;
+      }
+      med = g * 4;
+      for (;;) {
+        const int c = wcount(med);
+        if (below + c > kRank) break;
+        below += c;
         ++med;
       }
     }
@@ -110,44 +254,55 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
     for (int y = y_first; y < y_end; ++y) {
       if (col_ok) dst[(size_t)y * a.dst_step + x0 + lane] = (uint8_t)med;
       if (y + 1 >= y_end) break;
-      // prefetch the row entering the window
       const uint8_t *row = src + (size_t)clampi(y + 1 + R, 0, a.height - 1) * a.src_step;
-      const uint8_t na = row[gx_a];
-      const uint8_t nb = (lane < K - 1) ? row[gx_b] : (uint8_t)0;
-      // remove the oldest row
+      const uint32_t na = row[gx_a];
+      const uint32_t nb = has_b ? row[gx_b] : 0u;
+      // pixels leaving the window: this lane's output loses ring[slot][lane .. lane+K-1]
+      int d_below = 0;
 #pragma unroll
-      for (int dx = 0; dx < K; ++dx) {
-        const uint32_t v = ring[slot][lane + dx];
-        const uint32_t ad = hist_addr(v, lane);
-        hist[ad] = hist[ad] - 1;
-        below -= ((int)v < med) ? 1 : 0;
+      for (int dx = 0; dx < K; ++dx) d_below -= ((int)ring[slot][lane + dx] < med) ? 1 : 0;
+      {
+        const uint32_t oa = col_off(ring[slot][lane]), ia = col_off(na);  // column histograms: one out, one in
+        own_a[oa] = own_a[oa] - 1;
+        own_a[ia] = own_a[ia] + 1;
+        if (has_b) {
+          const uint32_t ob = col_off(ring[slot][32 + lane]), ib = col_off(nb);
+          own_b[ob] = own_b[ob] - 1;
+          own_b[ib] = own_b[ib] + 1;
+        }
       }
       __syncwarp();
-      ring[slot][lane] = na;
-      if (lane < K - 1) ring[slot][32 + lane] = nb;
+      ring[slot][lane] = (uint8_t)na;
+      if (has_b) ring[slot][32 + lane] = (uint8_t)nb;
       __syncwarp();
-      // add the new row
 #pragma unroll
-      for (int dx = 0; dx < K; ++dx) {
-        const uint32_t v = ring[slot][lane + dx];
-        const uint32_t ad = hist_addr(v, lane);
-        hist[ad] = hist[ad] + 1;
-        below += ((int)v < med) ? 1 : 0;
-      }
+      for (int dx = 0; dx < K; ++dx) d_below += ((int)ring[slot][lane + dx] < med) ? 1 : 0;
+      below += d_below;
       slot = (slot + 1 == K) ? 0 : slot + 1;
-      // re-centre: invariant below <= kRank < below + hist[med]
+      // re-centre: invariant below <= kRank < below + W(med)
       while (below > kRank) {
         --med;
-        below -= hist[hist_addr(med, lane)];
+        below -= wcount(med);
       }
       for (;;) {
-        const int hm = hist[hist_addr(med, lane)];
-        if (below + hm > kRank) break;
-        below += hm;
+        const int c = wcount(med);
+        if (below + c > kRank) break;
+        below += c;
         ++med;
       }
     }
   }
+}
+
+template <int K>
+cudaError_t launch_col(const MedianArgs &a, int sm_count, cudaStream_t s) {
+  const size_t smem = (size_t)kColWarps * kColHistBytes + (size_t)kColWarps * K * kRingPitch;
+  cudaError_t e = cudaFuncSetAttribute(median_col_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const uint64_t ctas = ((uint64_t)a.total_units + kColWarps - 1) / kColWarps;
+  const uint64_t cap = (uint64_t)sm_count * 3;
+  median_col_kernel<K><<<(int)(ctas < cap ? ctas : cap), kColThreads, smem, s>>>(a);
+  return cudaGetLastError();
 }
 
 template <int K>
@@ -191,6 +346,17 @@ cudaError_t launch_median_u8(const MedianLaunch &L, cudaStream_t stream, int *la
   const uint64_t cap = (uint64_t)L.sm_count * 6;
   const int grid = (int)(ctas < cap ? ctas : cap);
   if (launches) *launches = 1;
+  if (L.variant == 1) {
+    switch (L.ksize) {
+      case 3: return launch_col<3>(a, L.sm_count, stream);
+      case 5: return launch_col<5>(a, L.sm_count, stream);
+      case 7: return launch_col<7>(a, L.sm_count, stream);
+      case 9: return launch_col<9>(a, L.sm_count, stream);
+      case 11: return launch_col<11>(a, L.sm_count, stream);
+      case 13: return launch_col<13>(a, L.sm_count, stream);
+      default: return launch_col<15>(a, L.sm_count, stream);
+    }
+  }
   switch (L.ksize) {
     case 3: return launch_k<3>(a, grid, stream);
     case 5: return launch_k<5>(a, grid, stream);

@@ -48,16 +48,20 @@ def test_mono8_4k(ctx, q):
     assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, q), "4K mono8")
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("ksize", [3, 5, 11, 15])
 @pytest.mark.parametrize("w,h", [(96, 64), (7, 5), (333, 222), (32, 300), (1, 40), (40, 1)])
-def test_median_kernel_full_frame(ctx, ksize, w, h):
+def test_median_kernel_full_frame(ctx, ksize, w, h, variant):
+    """variant 0: per-thread window histogram; variant 1: column histograms."""
     import torch
+    ctx.set_tuning("median_variant", variant)
     img = synth.s1_uniform(h, w, 14 + ksize)
     d_src = torch.from_numpy(img).cuda()
     d_dst = torch.zeros_like(d_src)
     torch.cuda.synchronize()
     ctx.median_u8_device(d_src.data_ptr(), w, h, w, d_dst.data_ptr(), w, ksize)
     ctx.sync()
+    ctx.set_tuning("median_variant", 0)
     assert_same_bits(d_dst.cpu().numpy(), oracle.median_blur(img, ksize), f"median {ksize} {w}x{h}")
 
 
@@ -76,8 +80,10 @@ def test_median_golden_cv2(ctx):
             assert_same_bits(d_dst.cpu().numpy(), g[f"m{k}_{i}"], f"cv2 median {k} #{i}")
 
 
-def test_median_smooth_and_constant(ctx):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_median_smooth_and_constant(ctx, variant):
     import torch
+    ctx.set_tuning("median_variant", variant)
     for img in (np.full((100, 100), 255, np.uint8), np.zeros((64, 64), np.uint8),
                 np.tile(np.arange(200, dtype=np.uint8), (120, 1)), synth.s2_scene(480, 752, 15)):
         h, w = img.shape
@@ -87,6 +93,17 @@ def test_median_smooth_and_constant(ctx):
         ctx.median_u8_device(d_src.data_ptr(), w, h, w, d_dst.data_ptr(), w, 11)
         ctx.sync()
         assert_same_bits(d_dst.cpu().numpy(), oracle.median_blur(np.ascontiguousarray(img), 11), "median")
+    ctx.set_tuning("median_variant", 0)
+
+
+def test_mono8_callback_with_column_median(ctx, q):
+    ctx.set_tuning("median_variant", 1)
+    try:
+        for w, h, kind in [(752, 480, "s2"), (665, 665, "s1"), (131, 203, "s2")]:
+            img = synth.s2_scene(h, w, 17) if kind == "s2" else synth.s1_uniform(h, w, 17)
+            assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, q), f"{w}x{h} {kind}")
+    finally:
+        ctx.set_tuning("median_variant", 0)
 
 
 def test_mono8_device_batch(ctx, q):
