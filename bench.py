@@ -263,10 +263,12 @@ def run_ours(args):
             checks["first"] = cloud.bytes_view()[:32].copy()
             checks["width"] = cloud.width
 
-    def e2e_step(n):
-        ctx.process_stream(pin.array, collect=False, sink=sink, n_frames=n)
+    def e2e_step(n, check=False):
+        # the timed call hands every cloud to a NULL sink inside the C ABI (no Python per frame);
+        # the warm-up call looks at one cloud so a broken pipeline can not post a number
+        ctx.process_stream(pin.array, collect=False, sink=sink if check else None, n_frames=n)
 
-    e2e_step(host_ring)  # warm-up: allocates the slot buffers
+    e2e_step(host_ring, check=True)  # warm-up: allocates the slot buffers
     barrier_sync(world)
     t0 = time.perf_counter()
     e2e_step(e2e_frames)
