@@ -44,7 +44,7 @@ struct PinBuf {
 
 struct Slot {
   PinBuf h_in, h_out;
-  DevBuf d_in, d_med, d_out, d_scratch, d_tables;
+  DevBuf d_in, d_med, d_out, d_scratch, d_tables, d_cells;
   uint32_t *d_count = nullptr;  // [0] = kept points, [1] = compaction ticket
   uint32_t *h_count = nullptr;  // pinned
   cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr;
@@ -68,7 +68,7 @@ struct d2pc_ctx {
   uint64_t launches = 0;
   std::string last_cuda_error;
   // device-entry scratch
-  DevBuf d_scratch, d_tables, d_med_batch;
+  DevBuf d_scratch, d_tables, d_cells, d_med_batch;
   uint32_t *d_ticket = nullptr;
   // fusion buffers
   DevBuf d_fuse_in[4], d_container, d_combined, d_fused;
@@ -181,7 +181,8 @@ bool is_pinned_host(const void *p) {
 // Enqueue [median] + reproject for one frame batch already on the device.
 int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_frames, uint32_t w, uint32_t h,
                     size_t step, size_t frame_stride, uint8_t *d_med, uint8_t *d_out, size_t out_stride,
-                    uint32_t *d_counts, void *scratch, void *tables, uint32_t *ticket, cudaStream_t stream) {
+                    uint32_t *d_counts, void *scratch, void *tables, void *cells, uint32_t *ticket,
+                    cudaStream_t stream) {
   const d2pc_config &c = ctx->cfg;
   const uint8_t *reproj_in = d_in;
   int nl = 0;
@@ -226,6 +227,7 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
   L.compact = c.filter_mode == D2PC_FILTER_CROP_FINITE;
   L.scratch = scratch;
   L.tables = tables;
+  L.cells = cells;
   L.ticket = ticket;
   L.epoch = L.compact ? next_epoch(ctx) : 0;
   L.sm_count = ctx->sm_count;
@@ -276,7 +278,8 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   if ((rc = grow_dev(ctx, s.d_out, n * 16 + 16))) return rc;
   if ((rc = grow_pin(ctx, s.h_out, n * 16 + 16))) return rc;
   if (compact && ((rc = grow_dev(ctx, s.d_scratch, reproject_scratch_bytes(1, w, h, ctx->cfg.border), true)) ||
-                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(w, h)))))
+                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(w, h))) ||
+                  (rc = grow_dev(ctx, s.d_cells, reproject_cells_bytes(1, w, h, ctx->cfg.border)))))
     return rc;
 
   // ---- H2D (stream 1).  Pinned caller memory is DMA'd in place; pageable memory is staged.
@@ -315,7 +318,7 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   // ---- kernels (stream 2)
   CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
   rc = enqueue_kernels(ctx, s.d_in.p, is_f32, 1, w, h, d_pitch, d_pitch * h, s.d_med.p, s.d_out.p, n * 16 + 16,
-                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
+                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_cells.p, s.d_count + 1, ctx->s_compute);
   if (rc) return rc;
   CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
 
@@ -495,13 +498,14 @@ void d2pc_destroy(d2pc_ctx *ctx) {
   for (auto &s : ctx->slots) {
     free_pin(s.h_in), free_pin(s.h_out);
     free_dev(s.d_in), free_dev(s.d_med), free_dev(s.d_out), free_dev(s.d_scratch), free_dev(s.d_tables);
+    free_dev(s.d_cells);
     if (s.d_count) cudaFree(s.d_count);
     if (s.h_count) cudaFreeHost(s.h_count);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
     if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
   }
-  free_dev(ctx->d_scratch), free_dev(ctx->d_tables), free_dev(ctx->d_med_batch);
+  free_dev(ctx->d_scratch), free_dev(ctx->d_tables), free_dev(ctx->d_cells), free_dev(ctx->d_med_batch);
   for (auto &b : ctx->d_fuse_in) free_dev(b);
   free_dev(ctx->d_container), free_dev(ctx->d_combined), free_dev(ctx->d_fused);
   free_pin(ctx->h_fused), free_pin(ctx->h_combined);
@@ -670,10 +674,12 @@ static int reproject_device_common(d2pc_ctx *ctx, const void *d_in, bool is_f32,
   int rc;
   if (compact) {
     const size_t need = reproject_scratch_bytes(n_frames, w, h, ctx->cfg.border);
-    if (need > ctx->d_scratch.cap || reproject_table_bytes(w, h) > ctx->d_tables.cap) {
+    const size_t need_cells = reproject_cells_bytes(n_frames, w, h, ctx->cfg.border);
+    if (need > ctx->d_scratch.cap || reproject_table_bytes(w, h) > ctx->d_tables.cap || need_cells > ctx->d_cells.cap) {
       CU(ctx, cudaStreamSynchronize(ctx->s_compute));
       if ((rc = grow_dev(ctx, ctx->d_scratch, need, true)) ||
-          (rc = grow_dev(ctx, ctx->d_tables, reproject_table_bytes(w, h))))
+          (rc = grow_dev(ctx, ctx->d_tables, reproject_table_bytes(w, h))) ||
+          (rc = grow_dev(ctx, ctx->d_cells, need_cells)))
         return rc;
     }
   }
@@ -687,7 +693,8 @@ static int reproject_device_common(d2pc_ctx *ctx, const void *d_in, bool is_f32,
     d_med = ctx->d_med_batch.p;
   }
   return enqueue_kernels(ctx, static_cast<const uint8_t *>(d_in), is_f32, n_frames, w, h, step, frame_stride, d_med,
-                         d_points, points_stride, d_counts, ctx->d_scratch.p, ctx->d_tables.p, ctx->d_ticket, ctx->s_compute);
+                         d_points, points_stride, d_counts, ctx->d_scratch.p, ctx->d_tables.p, ctx->d_cells.p, ctx->d_ticket,
+                         ctx->s_compute);
 }
 
 int d2pc_reproject_f32_device(d2pc_ctx *ctx, const float *d_disp, uint32_t n_frames, uint32_t w, uint32_t h,
@@ -983,10 +990,11 @@ int d2pc_fuse_then_process(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, 
       (rc = grow_pin(ctx, s.h_out, n * 16 + 16)))
     return rc;
   if (compact && ((rc = grow_dev(ctx, s.d_scratch, reproject_scratch_bytes(1, fw, fh, ctx->cfg.border), true)) ||
-                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(fw, fh)))))
+                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(fw, fh))) ||
+                  (rc = grow_dev(ctx, s.d_cells, reproject_cells_bytes(1, fw, fh, ctx->cfg.border)))))
     return rc;
   rc = enqueue_kernels(ctx, ctx->d_fused.p, false, 1, fw, fh, fw, (size_t)fw * fh, s.d_med.p, s.d_out.p, n * 16 + 16,
-                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
+                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_cells.p, s.d_count + 1, ctx->s_compute);
   if (rc) return rc;
   uint64_t kept = n;
   if (compact) {

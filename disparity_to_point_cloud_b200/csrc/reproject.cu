@@ -52,6 +52,7 @@ struct ReprojArgs {
   const double *xtab, *ytab;  // (double)(float)(u + q03), (double)(float)(v + q13)
   uint32_t d_sure_bits;       // float bits of the smallest |d| whose point is certainly finite (rect0 compaction)
   int band_rows, cw_pad, band_groups, group_rows;  // band kernel geometry
+  uint32_t *cell_cnt;         // two-pass variant: per (frame, row, segment) survivor counts -> exclusive offsets
   QParams Q;
 };
 
@@ -72,6 +73,20 @@ __device__ __forceinline__ void st_stream_f4_if(float4 *p, const float4 &v, bool
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(p),
       "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred)
       : "memory");
+}
+
+// One pixel slot of a warp goes to out[pos + rank]: rank by ballot + popc, with the (very common) all-kept and
+// none-kept slots short-circuited by a warp-uniform test.  Returns pos advanced by the number of points stored.
+__device__ __forceinline__ uint32_t store_ranked(float4 *out, uint32_t pos, const float4 &p, bool keep, int lane,
+                                                 uint32_t lt_mask) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+  if (bal == 0xffffffffu) {
+    __stcs(out + (pos + (uint32_t)lane), p);
+    return pos + 32u;
+  }
+  if (bal == 0u) return pos;
+  if (keep) __stcs(out + (pos + (uint32_t)__popc(bal & lt_mask)), p);
+  return pos + (uint32_t)__popc(bal);
 }
 
 // src/disparity_to_point_cloud.cpp:61 -- convertTo(CV_32FC1, 1/8): float(src)*alpha + 0
@@ -228,6 +243,185 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(co
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (c_base + 32 * k + lane < a.cw) st_stream_f4(o + 32 * k, p[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CROP_FINITE, two-pass variant (rectified Q with q33 == +-0): count -> scan -> reproject + compacted store
+// ---------------------------------------------------------------------------
+// Whether a point survives is decided by its disparity alone for this Q (see the classify-first kernel below), so
+// a first kernel only READS the disparities and counts the survivors of every (row, 128-column) cell, a small scan
+// kernel turns the counts into output offsets, and the second kernel is the CROP kernel with one change: a cell's
+// survivors are stored from its offset with __ballot_sync + popc ranks.  The disparity is read twice
+// (24 instead of 20 bytes per pixel) but no kernel waits on another CTA and the heavy kernel keeps the CROP
+// kernel's full occupancy and straight-line inner loop.
+__device__ __forceinline__ bool keep_by_disparity(uint32_t mag, uint32_t sure_lo, uint32_t sure_span) {
+  return (mag - sure_lo) < sure_span;  // d_sure <= |d| < inf
+}
+
+template <typename InT, bool kVec>
+__global__ void __launch_bounds__(kThreads, 8) compact_count_kernel(const __grid_constant__ ReprojArgs a) {
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const uint32_t unit = blockIdx.x * kWarpsPerCta + wic;
+  if (unit >= a.total_units) return;
+  const uint32_t f = unit / a.units_per_frame;
+  const uint32_t rem = unit - f * a.units_per_frame;
+  const int rb = rem / a.n_seg, seg = rem - rb * a.n_seg;
+  const int c_base = seg * kSegCols, r_base = rb * a.rows_per_unit;
+  const int rows = min(a.rows_per_unit, a.ch - r_base);
+  const uint32_t sure_lo = a.d_sure_bits, sure_span = 0x7f800000u - a.d_sure_bits;
+  const uint8_t *in_row = a.in + (size_t)f * a.frame_stride + (size_t)(a.border + r_base) * a.step;
+  uint32_t *cell = a.cell_cnt + ((size_t)f * a.ch + r_base) * a.n_seg + seg;
+  const int c4 = c_base + 4 * lane;
+  for (int r = 0; r < rows; ++r, in_row += a.step, cell += a.n_seg) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};  // zero = dropped, also for pixels past the crop edge
+    if constexpr (kVec) {
+      if (c4 < a.cw) {
+        const float4 v = load4<InT>(in_row, a.border + c4, a.scale);
+        d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c4 + k < a.cw) d[k] = load1<InT>(in_row, a.border + c4 + k, a.scale);
+    }
+    uint32_t cnt = 0;
+    bool sliver = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t mag = (c4 + k < a.cw) ? (__float_as_uint(d[k]) & 0x7fffffffu) : 0u;
+      cnt += keep_by_disparity(mag, sure_lo, sure_span) ? 1u : 0u;
+      sliver |= (mag - 1u) < (sure_lo - 1u);
+    }
+    if (__builtin_expect(sliver, 0)) {  // 0 < |d| < d_sure: decided exactly
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t mag = (c4 + k < a.cw) ? (__float_as_uint(d[k]) & 0x7fffffffu) : 0u;
+        if ((mag - 1u) < (sure_lo - 1u))
+          cnt += point_is_finite(reproject_exact_slow(a.Q.q, a.border + c4 + k, a.border + r_base + r, d[k])) ? 1u : 0u;
+      }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) *cell = cnt;
+  }
+}
+
+// Exclusive scan of one frame's cell counts (row-major cells), in place; one CTA per frame, 1024 cells per step.
+__global__ void __launch_bounds__(1024) compact_scan_kernel(uint32_t *cell_cnt, uint32_t cells_per_frame,
+                                                            uint32_t *frame_counts) {
+  __shared__ uint32_t warp_excl[32];
+  __shared__ uint32_t chunk_total;
+  uint32_t *c = cell_cnt + (size_t)blockIdx.x * cells_per_frame;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t carry = 0;  // every thread keeps the same running total
+  for (uint32_t base = 0; base < cells_per_frame; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < cells_per_frame ? c[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_excl[wid] = incl;  // warp totals
+    __syncthreads();
+    if (wid == 0) {
+      const uint32_t w = warp_excl[lane];
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += n;
+      }
+      warp_excl[lane] = wi - w;
+      if (lane == 31) chunk_total = wi;
+    }
+    __syncthreads();
+    if (i < cells_per_frame) c[i] = carry + warp_excl[wid] + incl - v;
+    carry += chunk_total;
+    __syncthreads();  // warp_excl / chunk_total are rewritten by the next step
+  }
+  if (threadIdx.x == 0 && frame_counts) frame_counts[blockIdx.x] = carry;
+}
+
+// The CROP kernel's loop with offset stores: the survivors of cell (row, segment) go to out[offset(cell) + rank].
+template <typename InT, bool kVec>
+__global__ void __launch_bounds__(kThreads, 7) reproject_offsets_kernel(const __grid_constant__ ReprojArgs a) {
+  __shared__ __align__(16) float stage[kWarpsPerCta][2][kSegCols];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const QParams &Q = a.Q;
+  const uint32_t unit = blockIdx.x * kWarpsPerCta + wic;
+  if (unit >= a.total_units) return;
+  const uint32_t f = unit / a.units_per_frame;
+  const uint32_t rem = unit - f * a.units_per_frame;
+  const int rb = rem / a.n_seg, seg = rem - rb * a.n_seg;
+  const int c_base = seg * kSegCols, r_base = rb * a.rows_per_unit;
+  const int rows = min(a.rows_per_unit, a.ch - r_base);
+  const uint32_t sure_lo = a.d_sure_bits, sure_span = 0x7f800000u - a.d_sure_bits;
+
+  double xd[4];
+  uint32_t xslow = Q.zd_slow ? 0xfu : 0u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    xd[k] = rect_axis_const(a.border + c_base + 32 * k + lane, Q.q03);
+    xslow |= rect_axis_slow(xd[k]) ? (1u << k) : 0u;
+  }
+  const double yd_lane = rect_axis_const(a.border + r_base + lane, Q.q13);
+  const uint8_t *in_row = a.in + (size_t)f * a.frame_stride + (size_t)(a.border + r_base) * a.step;
+  const uint32_t *cell = a.cell_cnt + ((size_t)f * a.ch + r_base) * a.n_seg + seg;  // exclusive offsets now
+  float4 *out_f = a.out + (size_t)f * a.out_frame_stride;
+
+  for (int r = 0; r < rows; r += 2, in_row += 2 * a.step, cell += 2 * a.n_seg) {
+    float dd[2][4];
+    if constexpr (kVec) {
+      const int c4 = c_base + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        *reinterpret_cast<float4 *>(&stage[wic][j][4 * lane]) =
+            (r + j < rows && c4 < a.cw) ? load4<InT>(in_row + (size_t)j * a.step, a.border + c4, a.scale)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dd[j][k] = stage[wic][j][32 * k + lane];
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c_base + 32 * k + lane;
+          dd[j][k] = (r + j < rows && c < a.cw) ? load1<InT>(in_row + (size_t)j * a.step, a.border + c, a.scale) : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (r + j >= rows) break;
+      const double yd = __shfl_sync(0xffffffffu, yd_lane, r + j);
+      float4 p[4];
+      points_of4<kMathRect0>(Q, xd, yd, xslow, rect_axis_slow(yd), a.border + c_base + lane, a.border + r_base + r + j,
+                             dd[j], p);
+      bool kp[4], any_sliver = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool in_crop = c_base + 32 * k + lane < a.cw;  // the vector tail may hold real pixels past the crop
+        const uint32_t mag = in_crop ? (__float_as_uint(dd[j][k]) & 0x7fffffffu) : 0u;
+        kp[k] = keep_by_disparity(mag, sure_lo, sure_span);
+        any_sliver |= (mag - 1u) < (sure_lo - 1u);
+      }
+      if (__builtin_expect(any_sliver, 0)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool in_crop = c_base + 32 * k + lane < a.cw;
+          if (in_crop && ((__float_as_uint(dd[j][k]) & 0x7fffffffu) - 1u) < (sure_lo - 1u)) kp[k] = point_is_finite(p[k]);
+        }
+      }
+      uint32_t pos = cell[(size_t)j * a.n_seg];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pos = store_ranked(out_f, pos, p[k], kp[k], lane, lt_mask);
     }
   }
 }
@@ -830,11 +1024,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
       }
       uint32_t pos = unit_off[r * n_seg + sgm];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, kp[k]);
-        st_stream_f4_if(out_f + (uint32_t)(pos + __popc(bal & lt_mask)), p[k], kp[k]);
-        pos += __popc(bal);
-      }
+      for (int k = 0; k < 4; ++k) pos = store_ranked(out_f, pos, p[k], kp[k], lane, lt_mask);
     }
   }
 }
@@ -946,6 +1136,12 @@ size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t heigh
   const uint64_t tiles = (cw > 0 && ch > 0) ? std::max<uint64_t>(compact_tiles_per_frame(cw, ch), (uint64_t)ch) : 0;
   return (size_t)(tiles * n_frames * 8 + 256);
 }
+// two-pass variant: one uint32 per (frame, crop row, 128-column segment)
+size_t reproject_cells_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border) {
+  const long cw = (long)width - 2L * border, ch = (long)height - 2L * border;
+  if (cw <= 0 || ch <= 0) return 256;
+  return (size_t)n_frames * (size_t)ch * (size_t)((cw + kSegCols - 1) / kSegCols) * 4 + 256;
+}
 // per-column / per-row numerator tables of the rectified path
 size_t reproject_table_bytes(uint32_t width, uint32_t height) { return ((size_t)width + kSegCols + height) * 8 + 64; }
 
@@ -1022,7 +1218,35 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
         memcpy(&a.d_sure_bits, &fs, 4);
       }
     }
-    if (a.d_sure_bits != 0 && L.compact_variant == 0) {
+    if (a.d_sure_bits != 0 && L.compact_variant == 4 && L.cells) {
+      // two-pass variant: count -> scan -> CROP-style kernel with offset stores
+      int rb = 8;
+      const uint64_t want_units = (uint64_t)L.sm_count * 32;
+      while (rb > 2 && (uint64_t)a.n_seg * ((ch + rb - 1) / rb) * L.n_frames < want_units) rb >>= 1;
+      a.rows_per_unit = rb;
+      a.n_rb = (int)((ch + rb - 1) / rb);
+      a.units_per_frame = (uint32_t)a.n_seg * (uint32_t)a.n_rb;
+      const uint64_t total_u = (uint64_t)a.units_per_frame * L.n_frames;
+      if (total_u > 0xffffffffull) return cudaErrorInvalidValue;
+      a.total_units = (uint32_t)total_u;
+      a.cell_cnt = static_cast<uint32_t *>(L.cells);
+      const int g = (int)((total_u + kWarpsPerCta - 1) / kWarpsPerCta);
+      const uint32_t cells_per_frame = (uint32_t)a.n_seg * (uint32_t)ch;
+#define D2PC_TWO_PASS(T)                                                                                   \
+  do {                                                                                                     \
+    if (vec) compact_count_kernel<T, true><<<g, kThreads, 0, stream>>>(a);                                 \
+    else compact_count_kernel<T, false><<<g, kThreads, 0, stream>>>(a);                                    \
+    compact_scan_kernel<<<L.n_frames, 1024, 0, stream>>>(a.cell_cnt, cells_per_frame, a.counts);           \
+    if (vec) reproject_offsets_kernel<T, true><<<g, kThreads, 0, stream>>>(a);                             \
+    else reproject_offsets_kernel<T, false><<<g, kThreads, 0, stream>>>(a);                                \
+  } while (0)
+      if (L.in_is_f32) D2PC_TWO_PASS(float);
+      else D2PC_TWO_PASS(uint8_t);
+#undef D2PC_TWO_PASS
+      if (launches) *launches += 3;
+      return cudaGetLastError();
+    }
+    if (a.d_sure_bits != 0 && (L.compact_variant == 0 || L.compact_variant == 3)) {
       // band geometry: R rows per CTA (<= ~46 KB of disparities, <= 512 units), split into row groups so that
       // (segments x groups) fills the 8 warps evenly
       a.cw_pad = a.n_seg * kSegCols;

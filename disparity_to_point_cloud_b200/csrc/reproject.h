@@ -37,6 +37,7 @@ struct ReprojectLaunch {
   // compaction scratch (device): tile descriptors, ticket counter, launch epoch
   void *scratch = nullptr;
   void *tables = nullptr;      // reproject_table_bytes(width, height)
+  void *cells = nullptr;       // reproject_cells_bytes(...): two-pass CROP_FINITE cell counts / offsets
   uint32_t *ticket = nullptr;
   uint32_t epoch = 1;
   int sm_count = 148;
@@ -46,12 +47,15 @@ struct ReprojectLaunch {
   bool force_scalar = false;   // exercise the unaligned load path
   bool force_generic = false;  // exercise the generic-Q exact path on a rectified Q
   int exact_variant = 0;       // rectified exact quotients: 0 = guarded multiply (7 FP64 ops), 1 = Markstein (15)
-  int compact_variant = 0;     // CROP_FINITE kernel: 0 = automatic (band), 1 = park-then-compact, 2 = classify-first
+  int compact_variant = 0;     // CROP_FINITE kernel: 0 = automatic (band where Q allows, else park), 1 = park-then-
+                               // compact, 2 = classify-first tiles, 3 = band (1-3: single pass, decoupled look-back),
+                               // 4 = two-pass count / scan / offset store (reads the disparity twice)
 };
 
 void make_qparams(const double q[16], QParams *out);
 size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border);
 size_t reproject_table_bytes(uint32_t width, uint32_t height);
+size_t reproject_cells_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border);
 cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int *launches);
 
 }  // namespace d2pc

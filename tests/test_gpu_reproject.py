@@ -216,13 +216,13 @@ def test_fast_mode_within_tolerance(ctx):
 
 
 # ---- CROP_FINITE (extension): order-preserving compaction ---------------------------------------
-@pytest.mark.parametrize("park", [0, 1, 2])
+@pytest.mark.parametrize("park", [0, 1, 2, 4])
 @pytest.mark.parametrize("w,h,kind", [(640, 480, "s2"), (1280, 720, "s2"), (333, 97, "s1"), (81, 81, "zeros"),
                                       (400, 300, "nozeros"), (2000, 90, "s2"), (700, 300, "special"),
                                       (3840, 200, "s2"), (208, 1200, "s2"), (85, 83, "s1"), (5000, 100, "s2")])
 def test_crop_finite_compaction(ctx, w, h, kind, park):
-    """compact_variant 0: band kernel (default for the rectified Q); 1: park-then-compact (any Q);
-    2: classify-first tile kernel."""
+    """compact_variant 0: band kernel (default for the rectified Q); 1: park-then-compact (any Q); 2: classify-first
+    tile kernel (0-2 are single-pass with decoupled look-back); 4: two-pass count / scan / offset store."""
     import disparity_to_point_cloud_b200 as d2pc
     ctx.set_q(_default_q())
     ctx.set_tuning("force_park", park)

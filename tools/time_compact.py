@@ -35,14 +35,14 @@ for (w, h, f, kind) in [(1280, 720, 64, "s3"), (1280, 720, 64, "s2"), (3840, 216
     d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
     d_cnt = torch.zeros(f, dtype=torch.int32, device="cuda")
     ctx.set_filter_mode(1)
-    for park, mb in ((0, 3), (0, 4)):
+    for park, mb in ((0, 0), (3, 4), (2, 4), (1, 4)):
         ctx.set_tuning("force_park", park)
         ctx.set_tuning("ctas_per_sm", mb)
         s = t(lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4, d_out.data_ptr(), n * 16,
                                                d_cnt.data_ptr()))
         kept = int(d_cnt.sum().item())
         by = 4 * n * f + 16 * kept
-        print(w, h, f, kind, ["band", "park", "classify"][park], "minB", mb,
+        print(w, h, f, kind, ["two-pass", "park", "classify", "band"][park], "minB", mb,
               "%.1f us  %.1f GB/s frac %.3f kept %.3f" % (s * 1e6, by / s / 1e9, by / s / 1e9 / 6534.8, kept / (n * f)))
     ctx.set_tuning("force_park", 0)
     ctx.set_tuning("ctas_per_sm", 0)
