@@ -382,6 +382,39 @@ def run_extras(ctx, stream, torch, d2pc, synth):
     dt = time.perf_counter() - t0
     out["config2_752x480_mono8_stream_e2e"] = {"frames/s": 1000 / dt, "Mpixel/s": 1000 * w * h / dt / 1e6}
     pin.free()
+    # config 5: four 1280x720 maps -> score preprocessing -> fuse -> median 3 -> trim -> DisparityCb (665x665)
+    w, h = 1280, 720
+    fctx = d2pc.Context(device=torch.cuda.current_device(), offset_x=-7, offset_y=15)
+    fstream = torch.cuda.ExternalStream(fctx.compute_stream())
+    four = [torch.from_numpy(synth.s2_scene(h, w, 200 + i)).cuda() for i in range(4)]
+    st, r1, r2, rc, dims = fctx.fuse_geometry(w, h)
+    n_sq, fw, fh = dims
+    d_fused = torch.empty((fh, fw), dtype=torch.uint8, device="cuda")
+    d_comb = torch.empty((n_sq, n_sq), dtype=torch.uint8, device="cuda")
+    d_pre = [torch.empty((n_sq, n_sq), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    npts = (fw - 80) * (fh - 80)
+    d_cloud = torch.empty(npts * 16, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    s = _time_launches(torch, fstream, lambda: fctx.fuse_device(four[0].data_ptr(), four[1].data_ptr(),
+                                                                four[2].data_ptr(), four[3].data_ptr(), w, h, w,
+                                                                d_fused.data_ptr(), d_comb.data_ptr()), 50)
+    out["config5_fuse_merge_median3_kernels"] = {"us": s * 1e6, "Mpixel/s (merged)": n_sq * n_sq / s / 1e6,
+                                                 "GB/s (6 n^2)": 6 * n_sq * n_sq / s / 1e9}
+    s = _time_launches(torch, fstream, lambda: [fctx.preprocess_score_device(four[2 + i].data_ptr(), w, h, w, i + 1,
+                                                                             d_pre[i].data_ptr()) for i in range(2)], 50)
+    out["config5_score_preprocess_x2_kernels"] = {"us": s * 1e6}
+    s = _time_launches(torch, fstream, lambda: fctx.reproject_mono8_device(d_fused.data_ptr(), 1, fw, fh, fw, fw * fh,
+                                                                           d_cloud.data_ptr(), npts * 16), 50)
+    out["config5_fused_665x665_callback_kernels"] = {"us": s * 1e6, "points": npts}
+    hfour = [synth.s2_scene(h, w, 200 + i) for i in range(4)]
+    fctx.fuse_then_process(*hfour)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        fctx.fuse_then_process(*hfour)
+    dt = (time.perf_counter() - t0) / 50
+    out["config5_fuse_then_process_host_e2e"] = {"ms": dt * 1e3, "frame_sets/s": 1 / dt,
+                                                 "note": "4 pageable 1280x720 frames in, 342225-point cloud out, synchronous"}
+    fctx.close()
     return out
 
 

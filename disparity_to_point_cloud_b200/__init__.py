@@ -354,6 +354,10 @@ class Context:
                     "d2pc_preprocess_score")
         return out.array().copy()
 
+    def preprocess_score_device(self, d_score, w, h, step, which, d_out):
+        self._check(lib().d2pc_preprocess_score_device(self._h, d_score, w, h, step, which, d_out),
+                    "d2pc_preprocess_score_device")
+
     def fuse_preprocessed(self, d1, d2, s1c, s2c):
         d1, d2 = (np.ascontiguousarray(a, dtype=np.uint8) for a in (d1, d2))
         s1c, s2c = (np.ascontiguousarray(a, dtype=np.uint8) for a in (s1c, s2c))
