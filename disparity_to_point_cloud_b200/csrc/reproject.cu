@@ -134,8 +134,15 @@ __device__ __forceinline__ void points_of4(const QParams &Q, const double (&xd)[
         if (slow[k]) p[k] = reproject_exact_slow(Q.q, u0 + 32 * k, v, d[k]);
     }
   } else if constexpr (kMath == kMathGeneric) {
+    bool slow[4];
+    const double dv = (double)v;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) p[k] = reproject_exact_generic(Q.q, u0 + 32 * k, v, d[k]);
+    for (int k = 0; k < 4; ++k) p[k] = reproject_exact_generic_guarded(Q.q, (double)(u0 + 32 * k), dv, d[k], slow[k]);
+    if (__builtin_expect(slow[0] || slow[1] || slow[2] || slow[3], 0)) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (slow[k]) p[k] = reproject_exact_slow(Q.q, u0 + 32 * k, v, d[k]);
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < 4; ++k) p[k] = reproject_fast(Q.qf, u0 + 32 * k, v, d[k]);
