@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
         L.d2pc_oracle_rotate_cw.restype = None
         L.d2pc_oracle_grad_filter.argtypes = [C.c_int] * 6
         L.d2pc_oracle_grad_filter.restype = C.c_int
+        L.d2pc_oracle_grad_filter_table.argtypes = [C.c_int, C.c_int, _u8p]
+        L.d2pc_oracle_grad_filter_table.restype = None
         L.d2pc_oracle_fuse_rule.argtypes = [C.c_int] * 5
         L.d2pc_oracle_fuse_rule.restype = C.c_int
         L.d2pc_oracle_fuse.argtypes = [_u8p, _u8p, _u8p, _u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
@@ -198,6 +200,13 @@ def rotate_cw(img: np.ndarray) -> np.ndarray:
 
 def grad_filter(d1, d2, s1, s2) -> int:
     return lib().d2pc_oracle_grad_filter(int(d1), int(d2), int(s1), int(s2), int(s1), int(s2))
+
+
+def grad_filter_table(s1, s2) -> np.ndarray:
+    """gradFilter for all (d1, d2) at fixed scores -> (256, 256) uint8, indexed [d1, d2]."""
+    out = np.empty((256, 256), dtype=np.uint8)
+    lib().d2pc_oracle_grad_filter_table(int(s1), int(s2), _p(out, _u8p))
+    return out
 
 
 def fuse_rule(mode, d1, d2, s1, s2) -> int:

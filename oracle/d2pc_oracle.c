@@ -356,6 +356,13 @@ int d2pc_oracle_grad_filter(int dist1, int dist2, int score1, int score2,
   return 0;
 }
 
+/* gradFilter for every (dist1, dist2) in [0,255]^2 at fixed scores: out[dist1*256 + dist2]. */
+void d2pc_oracle_grad_filter_table(int score1, int score2, uint8_t *out) {
+  for (int a = 0; a < 256; ++a)
+    for (int b = 0; b < 256; ++b)
+      out[a * 256 + b] = (uint8_t)d2pc_oracle_grad_filter(a, b, score1, score2, score1, score2);
+}
+
 /* depth_map_fusion.cpp:169-217 (weightedAverage :162 truncates its weights to
  * int and divides by zero whenever both scores are >= 1; it is left out, see
  * SURVEY.md section 2). */

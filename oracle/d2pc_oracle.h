@@ -107,6 +107,9 @@ void d2pc_oracle_rotate_cw(const uint8_t *src, int w, int h, size_t src_step,
 int d2pc_oracle_grad_filter(int dist1, int dist2, int score1, int score2,
                             int grad1, int grad2);
 
+/* gradFilter over all (dist1, dist2) at fixed scores; out[dist1*256 + dist2] (test helper). */
+void d2pc_oracle_grad_filter_table(int score1, int score2, uint8_t *out);
+
 /* src/depth_map_fusion.cpp:162-217, the alternate (unused) fusion rules,
  * selected by mode: 0 gradFilter, 1 maxDist, 2 maxDistUnlessBlack,
  * 3 betterScore, 4 onlyGood1, 5 onlyGoodAvg, 6 overlap, 7 blackToWhite. */

@@ -71,10 +71,12 @@ def test_exhaustive_grad_filter_over_d1_d2(ctx):
         n = 256
         dd1, dd2 = np.meshgrid(np.arange(n, dtype=np.uint8), np.arange(n, dtype=np.uint8), indexing="ij")
         src2 = np.ascontiguousarray(np.rot90(dd2, 1))   # the kernel reads map 2 rotated clockwise: cropped_2 == dd2
-        for sc1, sc2 in [(110, 110), (124, 110), (125, 10), (10, 20), (20, 10), (99, 100), (100, 99), (0, 0)]:
+        # gradFilter sees the scores only through s1<s2, s2<s1, s<100, s<125: these 36 pairs hit every class
+        levels = [0, 99, 100, 124, 125, 255]
+        for sc1, sc2 in [(a, b) for a in levels for b in levels] + [(110, 110), (10, 20), (20, 10)]:
             s1 = np.full((n, n), sc1, np.uint8)
             s2 = np.full((n, n), sc2, np.uint8)
-            want = np.array([[oracle.grad_filter(a, b, sc1, sc2) for b in range(n)] for a in range(n)], np.uint8)
+            want = oracle.grad_filter_table(sc1, sc2)
             fused, combined = ctx.fuse(dd1, src2, s1, s2)
             assert_same_bits(fused, want, f"scores {sc1},{sc2}")
             assert np.all(combined == min(sc1, sc2))
@@ -82,7 +84,7 @@ def test_exhaustive_grad_filter_over_d1_d2(ctx):
         for k in ("fuse_median_ksize", "fuse_crop_right", "fuse_crop_top", "fuse_crop_bottom"):
             ctx.set_tuning(k, restore[k])
         s1 = np.full((n, n), 110, np.uint8)
-        want = np.array([[oracle.grad_filter(a, b, 110, 110) for b in range(n)] for a in range(n)], np.uint8)
+        want = oracle.grad_filter_table(110, 110)
         fused, _ = ctx.fuse(dd1, src2, s1, s1)
         assert_same_bits(fused, oracle.median_blur(want, 3)[30:n - 10, 0:n - 40], "median + trim")
     finally:
