@@ -111,6 +111,7 @@ SYMBOLS = [
                                                C.c_void_p]),
     ("d2pc_fuse_preprocessed", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                          C.c_uint32, C.POINTER(Image), C.POINTER(Image)]),
+    ("d2pc_colorize_depth", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Image)]),
     ("d2pc_fuse_device", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                    C.c_size_t, C.c_void_p, C.c_void_p]),
     ("d2pc_fuse_then_process", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
@@ -367,6 +368,13 @@ class Context:
                                                  s2c.ctypes.data, w, h, w, C.byref(fused), C.byref(combined)),
                     "d2pc_fuse_preprocessed")
         return fused.array().copy(), combined.array().copy()
+
+    def colorize_depth(self, gray) -> np.ndarray:
+        a = np.ascontiguousarray(gray, dtype=np.uint8)
+        h, w = a.shape
+        out = Image()
+        self._check(lib().d2pc_colorize_depth(self._h, a.ctypes.data, w, h, w, C.byref(out)), "d2pc_colorize_depth")
+        return np.ctypeslib.as_array(out.data, shape=(h, 3 * w)).reshape(h, w, 3).copy()
 
     def fuse_device(self, d_d1, d_d2, d_s1, d_s2, w, h, step, d_fused, d_combined=0):
         self._check(lib().d2pc_fuse_device(self._h, d_d1, d_d2, d_s1, d_s2, w, h, step, d_fused, d_combined or None),

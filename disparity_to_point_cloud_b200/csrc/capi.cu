@@ -75,6 +75,9 @@ struct d2pc_ctx {
   PinBuf h_fused, h_combined;
   DevBuf d_score_in, d_score_scratch, d_score_out[2];
   PinBuf h_score[2];
+  DevBuf d_color_in, d_color_out, d_color_lut;
+  PinBuf h_color;
+  bool color_lut_ready = false;
   cudaEvent_t ev_fuse = nullptr;
   // tuning / test hooks
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0, median_variant = 0;
@@ -511,6 +514,7 @@ void d2pc_destroy(d2pc_ctx *ctx) {
   free_pin(ctx->h_fused), free_pin(ctx->h_combined);
   free_dev(ctx->d_score_in), free_dev(ctx->d_score_scratch), free_dev(ctx->d_score_out[0]), free_dev(ctx->d_score_out[1]);
   free_pin(ctx->h_score[0]), free_pin(ctx->h_score[1]);
+  free_dev(ctx->d_color_in), free_dev(ctx->d_color_out), free_dev(ctx->d_color_lut), free_pin(ctx->h_color);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->ev_fuse) cudaEventDestroy(ctx->ev_fuse);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -969,6 +973,29 @@ int d2pc_fuse_preprocessed(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, 
     combined->data = ctx->h_combined.p;
     combined->width = combined->height = combined->step = (uint32_t)g.n;
   }
+  return D2PC_OK;
+}
+
+int d2pc_colorize_depth(d2pc_ctx *ctx, const uint8_t *gray, uint32_t w, uint32_t h, uint32_t step, d2pc_image *out) {
+  if (!ctx || !gray || !out) return D2PC_ERR_INVALID_ARG;
+  if (w == 0 || h == 0 || step < w) return D2PC_ERR_BAD_DIMS;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->s_compute));
+  int rc;
+  const size_t pitch = align_up(w, kAlign), px = (size_t)w * h;
+  if ((rc = grow_dev(ctx, ctx->d_color_in, pitch * h)) || (rc = grow_dev(ctx, ctx->d_color_out, px * 3)) ||
+      (rc = grow_dev(ctx, ctx->d_color_lut, 1024)) || (rc = grow_pin(ctx, ctx->h_color, px * 3)))
+    return rc;
+  CU(ctx, cudaMemcpy2DAsync(ctx->d_color_in.p, pitch, gray, step, w, h, cudaMemcpyHostToDevice, ctx->s_compute));
+  int nl = 0;
+  CU(ctx, launch_colorize(ctx->d_color_in.p, pitch, (int)w, (int)h, ctx->d_color_lut.p, !ctx->color_lut_ready,
+                          ctx->d_color_out.p, ctx->s_compute, &nl));
+  ctx->color_lut_ready = true;
+  ctx->launches += nl;
+  CU(ctx, cudaMemcpyAsync(ctx->h_color.p, ctx->d_color_out.p, px * 3, cudaMemcpyDeviceToHost, ctx->s_compute));
+  CU(ctx, cudaStreamSynchronize(ctx->s_compute));
+  out->data = ctx->h_color.p;
+  out->width = w, out->height = h, out->step = 3 * w;
   return D2PC_OK;
 }
 

@@ -96,6 +96,43 @@ __global__ void __launch_bounds__(256) fuse_merge_kernel(const __grid_constant__
   }
 }
 
+// ---- debug colouriser: DepthMapFusion::colorizeDepth (src/depth_map_fusion.cpp:304-358) -----------------------
+// A pure function of the gray value, so a 256-entry table is built once on the device with the reference's float32
+// operation order (explicit roundings: nothing may be contracted into an FMA) and applied per pixel.
+__global__ void colorize_lut_kernel(uchar4 *lut) {
+  const int g = threadIdx.x;
+  const unsigned char d = (unsigned char)__double2int_rz(__dadd_rn(40.0, __dmul_rn(0.8, (double)g)));
+  const unsigned int H = 255 - (255 - d) * 280 / 255;
+  const unsigned int hi = (H / 60) % 6;
+  const float f = __fsub_rn(__fdiv_rn((float)H, 60.f), (float)(H / 60));
+  const float V = 1.f, p = 0.f;                       // S = V = 1: p = V*(1-S)
+  const float q = __fsub_rn(1.f, f);                  // V*(1 - f*S)
+  const float t = __fsub_rn(1.f, __fsub_rn(1.f, f));  // V*(1 - (1-f)*S)
+  float rx = 0.f, ry = 0.f, rz = 0.f;
+  if (hi == 0) rx = p, ry = t, rz = V;
+  if (hi == 1) rx = p, ry = V, rz = q;
+  if (hi == 2) rx = t, ry = V, rz = p;
+  if (hi == 3) rx = V, ry = q, rz = p;
+  if (hi == 4) rx = V, ry = p, rz = t;
+  if (hi == 5) rx = q, ry = p, rz = V;
+  auto to_u8 = [](float v) { return (unsigned char)__float2int_rz(__fmul_rn(fmaxf(0.f, fminf(v, 1.f)), 255.f)); };
+  uchar4 o = make_uchar4(to_u8(rx), to_u8(ry), to_u8(rz), 0);
+  if (d == 40) o = make_uchar4(0, 0, 0, 0);
+  lut[g] = o;
+}
+
+__global__ void colorize_apply_kernel(const uint8_t *gray, size_t step, int w, int h, const uchar4 *lut, uint8_t *rgb) {
+  __shared__ uchar4 s_lut[256];
+  s_lut[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+  const size_t n = (size_t)w * h;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / w), x = (int)(i - (size_t)y * w);
+    const uchar4 c = s_lut[gray[(size_t)y * step + x]];
+    rgb[3 * i + 0] = c.x, rgb[3 * i + 1] = c.y, rgb[3 * i + 2] = c.z;
+  }
+}
+
 void crop_to_square(int cols, int rows, int ox, int oy, int member_oy, int r[4]) {
   const int num_cols = cols - std::abs(ox), num_rows = rows - std::abs(oy);
   const int n = std::min(cols, rows) - std::max(std::abs(ox), std::abs(member_oy));  // :252-253 uses offset_y_
@@ -152,4 +189,18 @@ cudaError_t launch_fuse_merge(const FuseLaunch &L, cudaStream_t stream, int *lau
   return cudaGetLastError();
 }
 
+}  // namespace d2pc
+
+namespace d2pc {
+cudaError_t launch_colorize(const uint8_t *gray, size_t step, int w, int h, void *lut256x4, bool build_lut,
+                            uint8_t *rgb, cudaStream_t stream, int *launches) {
+  uchar4 *lut = static_cast<uchar4 *>(lut256x4);
+  int n = 0;
+  if (build_lut) colorize_lut_kernel<<<1, 256, 0, stream>>>(lut), ++n;
+  const size_t px = (size_t)w * h;
+  const int grid = (int)std::min<size_t>((px + 255) / 256, 148 * 8);
+  if (px) colorize_apply_kernel<<<grid, 256, 0, stream>>>(gray, step, w, h, lut, rgb), ++n;
+  if (launches) *launches = n;
+  return cudaGetLastError();
+}
 }  // namespace d2pc

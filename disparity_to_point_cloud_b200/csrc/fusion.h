@@ -28,4 +28,9 @@ struct FuseLaunch {
 };
 cudaError_t launch_fuse_merge(const FuseLaunch &L, cudaStream_t stream, int *launches);
 
+// DepthMapFusion::colorizeDepth (src/depth_map_fusion.cpp:304-358): gray w x h -> 3 bytes per pixel, dense.
+// lut256x4: 1 KB of device memory owned by the caller; build_lut on first use.
+cudaError_t launch_colorize(const uint8_t *gray, size_t step, int w, int h, void *lut256x4, bool build_lut,
+                            uint8_t *rgb, cudaStream_t stream, int *launches);
+
 }  // namespace d2pc

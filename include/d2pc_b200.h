@@ -255,6 +255,12 @@ int d2pc_fuse_device(d2pc_ctx *ctx, const uint8_t *d_d1, const uint8_t *d_d2, co
                      const uint8_t *d_s2, uint32_t width, uint32_t height, size_t step, uint8_t *d_fused,
                      uint8_t *d_combined);
 
+/* DepthMapFusion::colorizeDepth (src/depth_map_fusion.cpp:304-358), the RAINBOW_WITH_BLACK colouring of the
+ * node's debug views: mono8 in host memory -> 3 bytes per pixel in the byte order the reference stores (and labels
+ * "rgb8", :298-299).  out->width = width, out->step = 3 * width. */
+int d2pc_colorize_depth(d2pc_ctx *ctx, const uint8_t *gray, uint32_t width, uint32_t height, uint32_t step,
+                        d2pc_image *out);
+
 /* BASELINE config 5: fuse four host frames, then run the whole DisparityCb on
  * the fused map without leaving the device. */
 int d2pc_fuse_then_process(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,

@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
         L.d2pc_oracle_fuse.restype = C.c_int
         L.d2pc_oracle_score_preprocess.argtypes = [_u8p, C.c_int, C.c_int, C.c_size_t, _i32p, C.c_int, _u8p]
         L.d2pc_oracle_score_preprocess.restype = C.c_int
+        L.d2pc_oracle_colorize_depth.argtypes = [_u8p, C.c_int, C.c_int, C.c_size_t, _u8p]
+        L.d2pc_oracle_colorize_depth.restype = None
         L.d2pc_oracle_run_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, _f64p,
                                              _u8p, C.c_size_t, C.c_int]
         L.d2pc_oracle_run_frames.restype = C.c_size_t
@@ -239,6 +241,14 @@ def score_preprocess(frame: np.ndarray, rect, vertical: bool) -> np.ndarray:
     rc = lib().d2pc_oracle_score_preprocess(_p(frame, _u8p), w, h, w, _p(r, _i32p), 1 if vertical else 0, _p(out, _u8p))
     if rc != 0:
         raise ValueError("bad rectangle")
+    return out
+
+
+def colorize_depth(gray: np.ndarray) -> np.ndarray:
+    gray = np.ascontiguousarray(gray, dtype=np.uint8)
+    h, w = gray.shape
+    out = np.empty((h, w, 3), dtype=np.uint8)
+    lib().d2pc_oracle_colorize_depth(_p(gray, _u8p), w, h, w, _p(out, _u8p))
     return out
 
 

@@ -455,6 +455,37 @@ int d2pc_oracle_fuse(const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
 }
 
 /* ------------------------------------------------------------------------- */
+/* debug colouriser (depth_map_fusion.cpp:304-358)                            */
+/* ------------------------------------------------------------------------- */
+
+/* colorizeDepth: gray -> HSV rainbow (blue..red), black stays black.  The three bytes are stored in the order the
+ * reference writes them (Point3_<uchar>(b, g, r)) into an image it then labels "rgb8" (:298-299). */
+void d2pc_oracle_colorize_depth(const uint8_t *gray, int w, int h, size_t step, uint8_t *rgb) {
+  const double maxDisp = 255;
+  const float S = 1.f, V = 1.f;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const unsigned char d = (unsigned char)(40 + 0.8 * gray[(size_t)y * step + x]);
+      const unsigned int H = 255 - ((unsigned char)maxDisp - d) * 280 / (unsigned char)maxDisp;
+      const unsigned int hi = (H / 60) % 6;
+      const float f = H / 60.f - H / 60;
+      const float p = V * (1 - S), q = V * (1 - f * S), t = V * (1 - (1 - f) * S);
+      float rx = 0, ry = 0, rz = 0;
+      if (hi == 0) rx = p, ry = t, rz = V;
+      if (hi == 1) rx = p, ry = V, rz = q;
+      if (hi == 2) rx = t, ry = V, rz = p;
+      if (hi == 3) rx = V, ry = q, rz = p;
+      if (hi == 4) rx = V, ry = p, rz = t;
+      if (hi == 5) rx = q, ry = p, rz = V;
+      uint8_t *o = rgb + ((size_t)y * w + x) * 3;
+      o[0] = (unsigned char)(fmaxf(0.f, fminf(rx, 1.f)) * 255.f);
+      o[1] = (unsigned char)(fmaxf(0.f, fminf(ry, 1.f)) * 255.f);
+      o[2] = (unsigned char)(fmaxf(0.f, fminf(rz, 1.f)) * 255.f);
+      if (d == 40) o[0] = o[1] = o[2] = 0;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* matching-score preprocessing (depth_map_fusion.cpp:64-99)                  */
 /* ------------------------------------------------------------------------- */
 

@@ -142,6 +142,9 @@ int d2pc_oracle_fuse(const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
 int d2pc_oracle_score_preprocess(const uint8_t *frame, int w, int h, size_t step, const int rect[4], int vertical,
                                  uint8_t *out);
 
+/* src/depth_map_fusion.cpp:304-358 colorizeDepth (the RAINBOW_WITH_BLACK debug views); rgb is w*h*3 dense. */
+void d2pc_oracle_colorize_depth(const uint8_t *gray, int w, int h, size_t step, uint8_t *rgb);
+
 /* ---- CPU baseline helpers (bench.py cpu_baseline / --impl reference) ---- */
 
 /* Runs d2pc_oracle_disparity_cb_f32 (mono8 == 0) or _mono8 (mono8 != 0) over

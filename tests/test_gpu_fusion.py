@@ -124,3 +124,13 @@ def test_config5_fuse_then_reproject(ctx):
     fused, _ = oracle.fuse(d1, d2, s1, s2, -7, 15)
     assert fused.shape == (665, 665)
     assert_same_bits(got, oracle.disparity_cb_mono8(fused, q), "config 5")
+
+
+def test_debug_colouriser(ctx):
+    """DepthMapFusion::colorizeDepth: every gray level, and a scene."""
+    ramp = np.tile(np.arange(256, dtype=np.uint8), (3, 1))
+    assert_same_bits(ctx.colorize_depth(ramp), oracle.colorize_depth(ramp), "all gray levels")
+    img = synth.s2_scene(211, 333, 8)
+    got = ctx.colorize_depth(img)
+    assert_same_bits(got, oracle.colorize_depth(img), "scene")
+    assert np.all(got[img == 0] == 0)     # black stays black

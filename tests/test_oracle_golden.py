@@ -157,3 +157,12 @@ def test_score_preprocess_chain_cv2():
         _, r2 = oracle.crop_to_square(h, w, -ox, -oy, oy)
         assert_same_bits(oracle.score_preprocess(s1, r1, False), g[f"pre1_{i}"], f"MatchingScoreCb1 #{i}")
         assert_same_bits(oracle.score_preprocess(oracle.rotate_cw(s2), r2, True), g[f"pre2_{i}"], f"MatchingScoreCb2 #{i}")
+
+
+def test_colorize_depth_known_answers():
+    # src/depth_map_fusion.cpp:304-358, bytes in the order the reference stores them
+    ramp = np.arange(256, dtype=np.uint8).reshape(1, 256)
+    c = oracle.colorize_depth(ramp)[0]
+    assert tuple(c[0]) == (0, 0, 0) and tuple(c[1]) == (0, 0, 0)     # d = uchar(40 + 0.8 g) == 40 -> black
+    assert c[2:].max(axis=1).min() == 255                            # S = V = 1: one channel is always saturated
+    assert tuple(c[5]) == (0, 101, 255) and tuple(c[128]) == (46, 255, 0) and tuple(c[255]) == (255, 0, 12)
