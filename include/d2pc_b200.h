@@ -275,8 +275,12 @@ size_t d2pc_serialize_pointcloud2(const d2pc_ctx *ctx, const d2pc_cloud *cloud, 
 
 /* ---- diagnostics ---------------------------------------------------------------- */
 
-/* Tuning / test hook: integer knobs by name ("rows_per_unit", "ctas_per_sm", "median_strip", "force_scalar",
- * "force_generic", "median_ksize", "border", "offset_x", "offset_y", "fuse_rule").  Not needed in normal use. */
+/* Tuning / test hook: integer knobs by name.  Not needed in normal use.
+ *   kernels : "rows_per_unit", "ctas_per_sm", "median_strip", "median_variant" (0 window histogram, 1 column
+ *             histograms), "compact_variant" (0 auto, 1 park, 2 classify-first, 3 band, 4 two-pass),
+ *             "exact_variant" (0 guarded multiply, 1 Markstein), "force_scalar", "force_generic"
+ *   config  : "median_ksize", "border", "offset_x", "offset_y", "fuse_rule", "fuse_median_ksize",
+ *             "fuse_crop_left|right|top|bottom" */
 int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value);
 
 const char *d2pc_strerror(int status);
