@@ -89,6 +89,22 @@ __device__ __forceinline__ uint32_t store_ranked(float4 *out, uint32_t pos, cons
   return pos + (uint32_t)__popc(bal);
 }
 
+// Minimal-instruction form: no short-circuits, the lane mask comes from the special register.
+__device__ __forceinline__ uint32_t store_ranked_tight(float4 *out, uint32_t pos, const float4 &p, bool keep) {
+  uint32_t lt;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+  const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+  unsigned long long addr;  // out + (pos + rank) * 16 in one IMAD.WIDE
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(pos + (uint32_t)__popc(bal & lt)), "l"(out));
+  if (keep) __stcs(reinterpret_cast<float4 *>(addr), p);
+  return pos + (uint32_t)__popc(bal);
+}
+// |x|, |y|, |z| all below infinity (false for NaN): three chained float compares.
+__device__ __forceinline__ bool point_is_finite_fast(const float4 &p) {
+  const float inf = __uint_as_float(0x7f800000u);
+  return fabsf(p.x) < inf && fabsf(p.y) < inf && fabsf(p.z) < inf;
+}
+
 // src/disparity_to_point_cloud.cpp:61 -- convertTo(CV_32FC1, 1/8): float(src)*alpha + 0
 __device__ __forceinline__ float u8_to_disp(uint32_t b, float scale) {
   return __fadd_rn(__fmul_rn((float)b, scale), 0.0f);
@@ -1016,22 +1032,11 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
       for (int k = 0; k < 4; ++k) dd[k] = dp[32 * k];
       float4 p[4];
       points_of4<kMathRect0>(Q, xd, yd, xslow, yslow, u0, a.border + row0 + r, dd, p);
-      // same three classes as step 2: sure -> kept, zero / inf / NaN -> dropped, sliver -> exact (rare)
-      bool kp[4], any_sliver = false;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t mag = __float_as_uint(dd[k]) & 0x7fffffffu;
-        kp[k] = (mag - sure_lo) < sure_span;
-        any_sliver |= (mag - 1u) < (sure_lo - 1u);
-      }
-      if (__builtin_expect(any_sliver, 0)) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (((__float_as_uint(dd[k]) & 0x7fffffffu) - 1u) < (sure_lo - 1u)) kp[k] = point_is_finite(p[k]);
-      }
+      // p is exact for every pixel, so "finite" is read off the result: it equals, class by class, what step 2
+      // counted from the disparity (sure -> finite, zero / inf / NaN -> not, sliver -> decided by the same exact path)
       uint32_t pos = unit_off[r * n_seg + sgm];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pos = store_ranked(out_f, pos, p[k], kp[k], lane, lt_mask);
+      for (int k = 0; k < 4; ++k) pos = store_ranked_tight(out_f, pos, p[k], point_is_finite_fast(p[k]));
     }
   }
 }
