@@ -52,6 +52,9 @@ struct ReprojArgs {
   const double *xtab, *ytab;  // (double)(float)(u + q03), (double)(float)(v + q13)
   uint32_t d_sure_bits;       // float bits of the smallest |d| whose point is certainly finite (rect0 compaction)
   int band_rows, cw_pad, band_groups, group_rows;  // band kernel geometry
+  int pipe_stages;            // pipeline kernel: shared-memory stages (tiles in flight per CTA); 0 = not used
+  int pipe_producers;         // pipeline kernel: producer warps per CTA (1, 2 or 4)
+  int pipe_consumers;         // pipeline kernel: consumer warps per CTA (8: three CTAs per SM, 12: two)
   uint32_t *cell_cnt;         // two-pass variant: per (frame, row, segment) survivor counts -> exclusive offsets
   QParams Q;
 };
@@ -162,6 +165,51 @@ __device__ __forceinline__ void points_of4(const QParams &Q, const double (&xd)[
   } else {
 #pragma unroll
     for (int k = 0; k < 4; ++k) p[k] = reproject_fast(Q.qf, u0 + 32 * k, v, d[k]);
+  }
+}
+
+// Compaction form of points_of4 for the rectified Q with q33 == +-0 (band kernel): only survivors are stored, so
+// the d == +-0 -> +-inf selects of the CROP form (and their per-column inf constants) are not computed at all.
+// Classes, from the disparity bits alone:
+//   fast   d_sure <= |d| < min(d_hi, inf): straight-line guarded multiply, the point is finite      -> kept
+//   rest   any other non-zero finite |d| (sliver below d_sure, or >= d_hi): exact slow path decides -> rare
+//   zero / inf / NaN disparity: never finite                                                       -> dropped
+// A lane that meets anything rare (a "rest" pixel, a quotient next to a float rounding boundary, a degenerate
+// row / column numerator) redoes its four pixels with the exact generic function, which is right for every
+// input; keep[] then equals, pixel by pixel, what the band kernel's counting step derived from the same bits.
+// The logic is spelled with unsigned arithmetic and one accumulated flag so that it stays in five predicates.
+__device__ __forceinline__ uint32_t midpoint_distance(double q) {  // <= 0x20 next to a float rounding boundary
+  return ((uint32_t)__double2loint(q) & 0x1fffffffu) - 0x0ffffff0u;
+}
+__device__ __forceinline__ void points_of4_keep(const QParams &Q, const double (&xd)[4], double yd, bool numer_slow,
+                                                int u0, int v, const float (&d)[4], uint32_t sure_lo,
+                                                uint32_t fast_span, float4 (&p)[4], bool (&keep)[4]) {
+  bool rare = numer_slow;
+  uint32_t cls[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t mag = __float_as_uint(d[k]) & 0x7fffffffu;
+    cls[k] = mag - sure_lo;  // fast class: cls < fast_span
+    rare |= (cls[k] >= fast_span) && ((mag - 1u) < 0x7f7fffffu);
+    const double w = __fma_rn(Q.q32, (double)d[k], 0.0);
+    const double r = rcp_1ulp_inrange(w);  // garbage (never a trap) outside the fast class
+    const double qx = __dmul_rn(xd[k], r), qy = __dmul_rn(yd, r), qz = __dmul_rn(Q.zd, r);
+    // (a garbage quotient that happens to look ambiguous only sends the lane to the exact path)
+    rare |= min(midpoint_distance(qx), min(midpoint_distance(qy), midpoint_distance(qz))) <= 0x20u;
+    p[k].x = __double2float_rn(qx);
+    p[k].y = __double2float_rn(qy);
+    p[k].z = __double2float_rn(qz);
+    p[k].w = 1.0f;  // pcl::PointXYZ's 4th float (cpp:74)
+  }
+  if (__builtin_expect(rare, 0)) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      p[k] = reproject_exact_slow(Q.q, u0 + 32 * k, v, d[k]);
+      keep[k] = (cls[k] < fast_span) || point_is_finite(p[k]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) keep[k] = cls[k] < fast_span;
   }
 }
 
@@ -857,6 +905,54 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_rect0_kern
 constexpr int kBandMaxUnits = 512;
 constexpr int kBandMaxRows = 16;
 
+// ---- mbarrier / TMA bulk-copy helpers (band and pipeline kernels)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(unsigned long long *bar, uint32_t parity) {  // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// Waiting consumers must not compete with the producer warps for issue slots: sleep between probes.
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  do {
+    __nanosleep(200);
+  } while (!mbar_try_wait(bar, parity));
+}
+// TMA bulk copy global -> shared (1-D, 16-byte aligned, size a multiple of 16), completion counted on an mbarrier
+__device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async_16_zfill(void *smem_dst, const void *gmem_src, uint32_t src_bytes) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
@@ -875,7 +971,15 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
   const QParams &Q = a.Q;
   const int R = a.band_rows, cwp = a.cw_pad, n_seg = a.n_seg;
 
-  if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+  constexpr bool kTma = kVec && sizeof(InT) == 4;  // aligned float rows: one TMA bulk copy per row
+  __shared__ __align__(8) unsigned long long bar_rows;
+  if (threadIdx.x == 0) {
+    s_tile = atomicAdd(a.ticket, 1u);
+    if constexpr (kTma) {
+      mbar_init(&bar_rows, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t f = tile / a.tiles_per_frame;
@@ -883,9 +987,33 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
   const int row0 = (int)t_in_f * R;  // first crop row of the band
   const uint8_t *in_f = a.in + (size_t)f * a.frame_stride;
 
-  // ---- 1. band -> shared memory (columns outer, rows inner: everything but two pointers is loop-invariant)
+  // ---- 1. band -> shared memory
   const int rows_here = min(R, a.ch - row0);
-  for (int c4 = 4 * (int)threadIdx.x; c4 < cwp; c4 += 4 * kCThreads) {
+  if constexpr (kTma) {
+    // one cp.async.bulk per row, issued by a single thread, completion counted on an mbarrier; meanwhile all
+    // threads zero what the copies do not write (padding columns up to cw_pad, rows past the frame's last crop
+    // row), so that it classifies as "dropped" without any mask
+    const int cw4 = (a.cw + 3) & ~3;
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&bar_rows, (uint32_t)rows_here * (uint32_t)cw4 * 4u);
+      const uint8_t *src = in_f + (size_t)(a.border + row0) * a.step + (size_t)a.border * 4;
+      for (int r = 0; r < rows_here; ++r)
+        tma_load_1d(smem_u32(&sd[r * cwp]), src + (size_t)r * a.step, (uint32_t)cw4 * 4u, &bar_rows);
+    }
+    const int pad4 = (cwp - cw4) >> 2;  // float4 groups of padding per row
+    for (int t = (int)threadIdx.x; t < pad4 * rows_here; t += kCThreads) {
+      const int r = t / pad4, g4 = t - r * pad4;
+      *reinterpret_cast<float4 *>(&sd[r * cwp + cw4 + 4 * g4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int t = (int)threadIdx.x; t < (R - rows_here) * (cwp >> 2); t += kCThreads)
+      *reinterpret_cast<float4 *>(&sd[rows_here * cwp + 4 * t]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    mbar_wait(&bar_rows, 0);
+    if (a.cw & 3)  // the copy brought up to 3 real pixels past the crop edge: they must not be counted or kept
+      for (int t = (int)threadIdx.x; t < rows_here * 4; t += kCThreads)
+        if ((t & 3) >= (a.cw & 3)) sd[(t >> 2) * cwp + (a.cw & ~3) + (t & 3)] = 0.f;
+  }
+  // (cp.async / scalar staging for unaligned or mono8 rows: columns outer, rows inner)
+  for (int c4 = 4 * (int)threadIdx.x; !kTma && c4 < cwp; c4 += 4 * kCThreads) {
     const int left = min(max(a.cw - c4, 0), 4);  // crop pixels this 4-pixel group holds
     float *dst = &sd[c4];
     if constexpr (kVec && sizeof(InT) == 4) {
@@ -919,6 +1047,8 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
   // takes four adjacent pixels (one 16-byte shared-memory load) and the warp sums with a single REDUX.
   const int n_units = R * n_seg;
   const uint32_t sure_lo = a.d_sure_bits, sure_span = 0x7f800000u - a.d_sure_bits;
+  // straight-line class of step 5: d_sure <= |d| < min(d_hi, inf) (d_hi: see reproject_exact_rectified)
+  const uint32_t fast_span = max(min(Q.dhi_bits, 0x7f800000u), sure_lo) - sure_lo;
   for (int r = 0; r < R; ++r)
     for (int sgm = wic; sgm < n_seg; sgm += kCWarps) {
       const float4 d4 = *reinterpret_cast<const float4 *>(&sd[r * cwp + sgm * kSegCols + 4 * lane]);
@@ -1031,12 +1161,354 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
 #pragma unroll
       for (int k = 0; k < 4; ++k) dd[k] = dp[32 * k];
       float4 p[4];
-      points_of4<kMathRect0>(Q, xd, yd, xslow, yslow, u0, a.border + row0 + r, dd, p);
-      // p is exact for every pixel, so "finite" is read off the result: it equals, class by class, what step 2
-      // counted from the disparity (sure -> finite, zero / inf / NaN -> not, sliver -> decided by the same exact path)
+      bool kp[4];
+      points_of4_keep(Q, xd, yd, yslow || xslow != 0u, u0, a.border + row0 + r, dd, sure_lo, fast_span, p, kp);
       uint32_t pos = unit_off[r * n_seg + sgm];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pos = store_ranked_tight(out_f, pos, p[k], point_is_finite_fast(p[k]));
+      for (int k = 0; k < 4; ++k) pos = store_ranked_tight(out_f, pos, p[k], kp[k]);
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// CROP_FINITE, rectified Q with q33 == +-0, float32 rows, 16-byte aligned: warp-specialised pipeline kernel
+// ---------------------------------------------------------------------------
+// Same decomposition as the band kernel (a tile = R full crop rows, classify from the disparity, one look-back per
+// tile, survivors reprojected straight into place) but the phases run on different warps of a PERSISTENT CTA and
+// are decoupled by mbarriers, so no warp that does arithmetic ever waits for HBM or for another CTA:
+//   producer warps  claim a tile (atomic ticket), bring its rows into a shared-memory stage with TMA bulk copies
+//                   (cp.async.bulk, completion on an mbarrier), count the survivors of every (row, 128-column)
+//                   unit, scan the counts, publish the tile aggregate, run the decoupled look-back and hand the
+//                   stage to the consumers ("ready" mbarrier); loads for the next stages are already in flight;
+//   consumer warps  take (segment x rows) items of ready stages in a rotating order, reproject from shared memory
+//                   and store survivors at unit_offset + rank (ballot + popc); a stage returns to the producer
+//                   when all consumer warps have arrived on its "empty" mbarrier.
+// A producer only waits for consumers BEFORE it claims a ticket; once a tile is claimed its aggregate and prefix
+// are published without depending on any consumer, so the look-back chain always makes progress.
+constexpr int kPipeMaxStages = 12;
+constexpr int kPipeMaxUnits = 128;  // units per tile
+constexpr int kPipeMaxRows = 16;
+constexpr uint32_t kPipeNoTile = 0xffffffffu;
+
+struct PipeStageInfo {
+  uint32_t tile, excl, frame, rows, total;
+  int row0;
+};
+
+// Survivors of one (row, 128-column) unit, counted from the disparities alone (4 adjacent pixels per lane).
+__device__ __forceinline__ uint32_t count_unit_rect0(const QParams &Q, const float *unit, int lane, int u_base, int v,
+                                                    uint32_t sure_lo, uint32_t sure_span) {
+  const float4 d4 = *reinterpret_cast<const float4 *>(&unit[4 * lane]);
+  const uint32_t m0 = __float_as_uint(d4.x) & 0x7fffffffu, m1 = __float_as_uint(d4.y) & 0x7fffffffu;
+  const uint32_t m2 = __float_as_uint(d4.z) & 0x7fffffffu, m3 = __float_as_uint(d4.w) & 0x7fffffffu;
+  // sure class: d_sure <= |d| < inf
+  uint32_t cnt = ((m0 - sure_lo) < sure_span) + ((m1 - sure_lo) < sure_span) + ((m2 - sure_lo) < sure_span) +
+                 ((m3 - sure_lo) < sure_span);
+  // sliver class 0 < |d| < d_sure: decided exactly, rare
+  if (__builtin_expect(min(min(m0 - 1u, m1 - 1u), min(m2 - 1u, m3 - 1u)) < sure_lo - 1u, 0)) {
+    const int u = u_base + 4 * lane;
+    if ((m0 - 1u) < (sure_lo - 1u)) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 0, v, d4.x)) ? 1u : 0u;
+    if ((m1 - 1u) < (sure_lo - 1u)) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 1, v, d4.y)) ? 1u : 0u;
+    if ((m2 - 1u) < (sure_lo - 1u)) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 2, v, d4.z)) ? 1u : 0u;
+    if ((m3 - 1u) < (sure_lo - 1u)) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 3, v, d4.w)) ? 1u : 0u;
+  }
+  return __reduce_add_sync(0xffffffffu, cnt);
+}
+
+template <int kPW, int kCW>
+__global__ void __launch_bounds__((kCW + kPW) * 32, (kCW + kPW) * 32 <= 384 ? 3 : 2)
+    reproject_compact_pipe_kernel(const __grid_constant__ ReprojArgs a) {
+  extern __shared__ __align__(128) float pipe_stage[];  // [stages][R][cw_pad]
+  __shared__ __align__(8) unsigned long long bar_full[kPipeMaxStages], bar_ready[kPipeMaxStages], bar_empty[kPipeMaxStages];
+  __shared__ PipeStageInfo info[kPipeMaxStages];
+  __shared__ __align__(16) uint32_t unit_off[kPipeMaxStages][kPipeMaxUnits];
+  __shared__ double syd[kPipeMaxStages][kPipeMaxRows];
+  __shared__ uint32_t p_issued, p_flags;
+  __shared__ uint32_t lb_sum[kPW], lb_hit[kPW];
+
+  const QParams &Q = a.Q;
+  const int B = a.pipe_stages, R = a.band_rows, cwp = a.cw_pad, n_seg = a.n_seg;
+  const uint32_t stage_floats = (uint32_t)R * (uint32_t)cwp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sure_lo = a.d_sure_bits, sure_span = 0x7f800000u - a.d_sure_bits;
+
+  // every stage starts zeroed: TMA only ever writes columns [0, roundup4(cw)) of a row, so the padding up to
+  // cw_pad classifies as "dropped" for the whole kernel
+  for (uint32_t i = threadIdx.x; i < (uint32_t)B * stage_floats / 4; i += blockDim.x)
+    reinterpret_cast<float4 *>(pipe_stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < B; ++b) {
+      mbar_init(&bar_full[b], 1);
+      mbar_init(&bar_ready[b], 1);
+      mbar_init(&bar_empty[b], kCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async_smem();  // the zeroing (generic proxy) is ordered before the first TMA write (async proxy)
+  __syncthreads();
+
+  if (warp >= kCW) {
+    // =========================== producer group: issue, count, look-back ===========================
+    constexpr int kPT = kPW * 32;
+    const int ptid = (int)threadIdx.x - kCW * 32, pw = warp - kCW;
+    auto group_sync = [&]() {
+      if constexpr (kPW == 1) __syncwarp();
+      else asm volatile("bar.sync 1, %0;" ::"n"(kPT) : "memory");
+    };
+    const uint32_t total_tiles = a.tiles_per_frame * (uint32_t)a.n_frames;
+    const uint32_t row_copy_bytes = (uint32_t)((a.cw + 3) & ~3) * 4u;
+    // Three cursors over this CTA's tiles (the end marker counts as one): i issued (ticket claimed, TMA in
+    // flight), c scanned (the consumers' unit counts turned into offsets, aggregate published), j resolved
+    // (look-back done, handed to the consumers); j <= c <= i <= j + B.  Scanning runs ahead of resolving so that
+    // a tile's aggregate is public as soon as it has been counted -- other CTAs' look-backs never wait behind
+    // this CTA's own look-back.
+    uint32_t i = 0, c = 0, j = 0;
+    uint32_t bi = 0, use_i = 0, bc = 0, use_c = 0, bj = 0, use_j = 0;  // stage index / earlier uses of it, per cursor
+    bool exhausted = false, pending = false;
+    uint32_t pending_tile = 0;
+    for (;;) {
+      if (ptid == 0) {
+        // The ticket's round trip (an L2 atomic) is taken off the critical path: it is claimed once its stage is
+        // known to be free, and the rows are put in flight at the top of the NEXT step, when the value has
+        // arrived.  (A ticket is never held while waiting for a stage: that would stall every later tile.)
+        for (;;) {
+          if (pending) {
+            const uint32_t tile = pending_tile;
+            if (tile >= total_tiles) {
+              exhausted = true;
+              info[bi].tile = kPipeNoTile;
+            } else {
+              const uint32_t f = tile / a.tiles_per_frame, t_in_f = tile - f * a.tiles_per_frame;
+              const int row0 = (int)t_in_f * R, rows = min(R, a.ch - row0);
+              info[bi].tile = tile;
+              info[bi].frame = f;
+              info[bi].row0 = row0;
+              info[bi].rows = (uint32_t)rows;
+              mbar_arrive_expect_tx(&bar_full[bi], (uint32_t)rows * row_copy_bytes);
+              const uint8_t *src = a.in + (size_t)f * a.frame_stride + (size_t)(a.border + row0) * a.step + (size_t)a.border * 4;
+              const uint32_t dst = smem_u32(pipe_stage + (size_t)bi * stage_floats);
+              for (int r = 0; r < rows; ++r)
+                tma_load_1d(dst + (uint32_t)r * (uint32_t)cwp * 4u, src + (size_t)r * a.step, row_copy_bytes, &bar_full[bi]);
+            }
+            pending = false;
+            ++i;
+            if (++bi == (uint32_t)B) bi = 0, ++use_i;
+          }
+          if (exhausted || i >= j + (uint32_t)B) break;
+          if (use_i > 0) {  // the stage must have been drained by the consumers
+            const uint32_t par = (use_i - 1u) & 1u;
+            if (i == j) mbar_wait(&bar_empty[bi], par);            // nothing else to do: block
+            else if (!mbar_test_wait(&bar_empty[bi], par)) break;  // count / resolve something first
+          }
+          pending_tile = atomicAdd(a.ticket, 1u);
+          pending = true;
+          if (i != j) break;  // there is other work: pick the value up at the top of the next step
+        }
+        // next step: count the oldest uncounted tile if its rows have landed (or nothing is left to resolve)
+        uint32_t scan_next = 0;
+        if (c < i)
+          scan_next = (c == j || info[bc].tile == kPipeNoTile || mbar_test_wait(&bar_full[bc], use_c & 1u)) ? 1u : 0u;
+        p_issued = i;
+        p_flags = (exhausted ? 1u : 0u) | (scan_next << 1) | (pending ? 4u : 0u);
+      }
+      group_sync();
+      i = p_issued;
+      exhausted = (p_flags & 1u) != 0u;
+      const uint32_t p_flags_copy = p_flags;
+      const bool scan_next = (p_flags_copy & 2u) != 0u;
+      group_sync();  // p_issued / p_flags are rewritten at the top of the next iteration
+      if (j == i && (p_flags_copy & 4u) == 0u) break;  // (only once the tickets are exhausted)
+      if (scan_next) {
+        // ---- tile c: unit counts -> unit offsets, publish the aggregate
+        const uint32_t tile = info[bc].tile;
+        if (tile != kPipeNoTile) {
+          mbar_wait(&bar_full[bc], use_c & 1u);
+          const uint32_t f = info[bc].frame;
+          const int row0 = info[bc].row0, rows = (int)info[bc].rows;
+          const uint32_t t_in_f = tile - f * a.tiles_per_frame;
+          float *sd = pipe_stage + (size_t)bc * stage_floats;
+          if (a.cw & 3) {  // the copy brought up to 3 real pixels past the crop edge: they must not be counted
+            for (int t = ptid; t < rows * 4; t += kPT)
+              if ((t & 3) >= (a.cw & 3)) sd[(t >> 2) * cwp + (a.cw & ~3) + (t & 3)] = 0.f;
+            fence_proxy_async_smem();
+            group_sync();
+          }
+          if (ptid >= kPT - rows) {  // row numerators (last lanes of the group); NaN marks a row the straight-line
+            const int r = kPT - 1 - ptid;  // path must not use
+            const double y = rect_axis_const(a.border + row0 + r, Q.q13);
+            syd[bc][r] = rect_axis_slow(y) ? __longlong_as_double(0x7ff8000000000000ll) : y;
+          }
+          // survivors per unit from the disparity alone.  The stage is a flat array of units (cw_pad = n_seg * 128,
+          // so unit u starts at float 128 * u); a warp takes four consecutive units at a time, each lane counts
+          // its 4 pixels of every unit into one byte of a word, and a single REDUX adds all four units at once
+          // (a unit has 128 pixels, so no byte can carry into the next).
+          {
+            const int n_units = rows * n_seg;
+            for (int u0 = 4 * pw; u0 < n_units; u0 += 4 * kPW) {
+              uint32_t packed = 0;
+              bool rare = false;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (u0 + q < n_units) {
+                  const float4 d4 = *reinterpret_cast<const float4 *>(&sd[(u0 + q) * kSegCols + 4 * lane]);
+                  const uint32_t m0 = __float_as_uint(d4.x) & 0x7fffffffu, m1 = __float_as_uint(d4.y) & 0x7fffffffu;
+                  const uint32_t m2 = __float_as_uint(d4.z) & 0x7fffffffu, m3 = __float_as_uint(d4.w) & 0x7fffffffu;
+                  const uint32_t cq = ((m0 - sure_lo) < sure_span) + ((m1 - sure_lo) < sure_span) +
+                                      ((m2 - sure_lo) < sure_span) + ((m3 - sure_lo) < sure_span);
+                  rare |= min(min(m0 - 1u, m1 - 1u), min(m2 - 1u, m3 - 1u)) < sure_lo - 1u;  // sliver 0 < |d| < d_sure
+                  packed |= cq << (8 * q);
+                }
+              }
+              if (__builtin_expect(rare, 0)) {  // slivers are decided by the exact path
+#pragma unroll 1
+                for (int q = 0; q < 4 && u0 + q < n_units; ++q) {
+                  const int r = (u0 + q) / n_seg, sgm = (u0 + q) - r * n_seg;
+                  const float *px = &sd[(u0 + q) * kSegCols + 4 * lane];
+#pragma unroll 1
+                  for (int e = 0; e < 4; ++e) {
+                    const uint32_t m = __float_as_uint(px[e]) & 0x7fffffffu;
+                    if ((m - 1u) < (sure_lo - 1u) &&
+                        point_is_finite(reproject_exact_slow(Q.q, a.border + sgm * kSegCols + 4 * lane + e,
+                                                             a.border + row0 + r, px[e])))
+                      packed += 1u << (8 * q);
+                  }
+                }
+              }
+              packed = __reduce_add_sync(0xffffffffu, packed);
+              if (lane < 4 && u0 + lane < n_units) unit_off[bc][u0 + lane] = (packed >> (8 * lane)) & 0xffu;
+            }
+          }
+          group_sync();
+          if (pw == 0) {  // exclusive scan of <= 128 unit counts, four per lane
+            const int n_units = rows * n_seg;
+            uint4 u4 = *reinterpret_cast<const uint4 *>(&unit_off[bc][4 * lane]);
+            if (4 * lane + 0 >= n_units) u4.x = 0;
+            if (4 * lane + 1 >= n_units) u4.y = 0;
+            if (4 * lane + 2 >= n_units) u4.z = 0;
+            if (4 * lane + 3 >= n_units) u4.w = 0;
+            const uint32_t mine = u4.x + u4.y + u4.z + u4.w;
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += n;
+            }
+            const uint32_t e0 = incl - mine;
+            *reinterpret_cast<uint4 *>(&unit_off[bc][4 * lane]) =
+                make_uint4(e0, e0 + u4.x, e0 + u4.x + u4.y, e0 + u4.x + u4.y + u4.z);
+            if (lane == 31) {
+              info[bc].total = incl;
+              // the first tile of a frame starts the chain: its aggregate is its inclusive prefix
+              st_relaxed_u64(a.tile_desc + tile, desc_pack(a.epoch, t_in_f == 0 ? kFlagPrefix : kFlagAggregate, incl));
+            }
+          }
+        }
+        ++c;
+        if (++bc == (uint32_t)B) bc = 0, ++use_c;
+        continue;  // (the group_sync at the top of the loop orders unit_off / info / syd before any later use)
+      }
+      // ---- resolve tile j: decoupled look-back over the earlier tiles of its frame, kPT predecessors per step
+      const uint32_t tile = info[bj].tile;
+      if (tile == kPipeNoTile) {  // end marker: release the consumers
+        if (ptid == 0) mbar_arrive(&bar_ready[bj]);
+        break;
+      }
+      const uint32_t f = info[bj].frame, tile_total = info[bj].total;
+      const uint32_t t_in_f = tile - f * a.tiles_per_frame;
+      uint32_t excl = 0;
+      if (t_in_f != 0) {
+        int look = (int)t_in_f - 1;
+        for (;;) {
+          const int my = look - ptid;
+          uint32_t flag = kFlagPrefix, val = 0;  // positions before the frame start act as a zero prefix
+          if (my >= 0) {
+            unsigned long long dv;
+            do {
+              dv = ld_relaxed_u64(a.tile_desc + (tile - t_in_f) + my);
+            } while ((uint32_t)(dv >> 34) != a.epoch || ((dv >> 32) & 3u) == 0);
+            flag = (uint32_t)(dv >> 32) & 3u;
+            val = (uint32_t)dv;
+          }
+          const uint32_t pmask = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
+          const int stop = pmask ? (__ffs(pmask) - 1) : 32;
+          uint32_t contrib = (lane <= stop) ? val : 0u;
+          contrib = __reduce_add_sync(0xffffffffu, contrib);
+          bool done;
+          if constexpr (kPW == 1) {
+            excl += contrib;
+            done = pmask != 0u;
+          } else {
+            if (lane == 0) lb_sum[pw] = contrib, lb_hit[pw] = pmask ? 1u : 0u;
+            group_sync();
+            done = false;
+#pragma unroll
+            for (int w = 0; w < kPW; ++w)
+              if (!done) {
+                excl += lb_sum[w];
+                done = lb_hit[w] != 0u;
+              }
+            group_sync();  // lb_* are rewritten by the next step / the next tile
+          }
+          if (done) break;
+          look -= kPT;
+        }
+        if (ptid == 0) st_relaxed_u64(a.tile_desc + tile, desc_pack(a.epoch, kFlagPrefix, excl + tile_total));
+      }
+      if (ptid == 0) {
+        if (t_in_f == a.tiles_per_frame - 1 && a.counts) a.counts[f] = excl + tile_total;
+        info[bj].excl = excl;
+        mbar_arrive(&bar_ready[bj]);  // release: unit_off, syd, info are visible to the waiting consumers
+      }
+      ++j;
+      if (++bj == (uint32_t)B) bj = 0, ++use_j;
+    }
+  } else {
+    // =========================== consumers: reproject + store ===========================
+    const int wic = warp;
+    const uint32_t fast_span = max(min(Q.dhi_bits, 0x7f800000u), sure_lo) - sure_lo;
+    uint32_t bj = 0, use_j = 0;
+    uint32_t g = (uint32_t)wic, base = 0;  // this warp's next item / first item of the current tile, numbered over
+                                           // all tiles of the CTA so that the warps rotate over the segments
+    for (;;) {
+      mbar_wait_backoff(&bar_ready[bj], use_j & 1u);
+      const uint32_t tile = info[bj].tile;
+      if (tile == kPipeNoTile) break;
+      mbar_wait(&bar_full[bj], use_j & 1u);  // (complete long ago: makes the TMA writes visible to this thread)
+      const uint32_t f = info[bj].frame, excl = info[bj].excl;
+      const int row0 = info[bj].row0, rows = (int)info[bj].rows;
+      float4 *out_f = a.out + (size_t)f * a.out_frame_stride + excl;
+      const float *sd = pipe_stage + (size_t)bj * stage_floats;
+      while (g < base + (uint32_t)n_seg) {
+        const int sgm = (int)(g - base);
+        const int u0 = a.border + sgm * kSegCols + lane;
+        double xd[4];
+        bool xslow = Q.zd_slow != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          xd[k] = __ldg(&a.xtab[u0 + 32 * k]);  // NaN marks a column the straight-line path must not use
+          xslow |= ((uint32_t)__double2hiint(xd[k]) & 0x7ff00000u) == 0x7ff00000u;
+        }
+        for (int r = 0; r < rows; ++r) {
+          const double yd = syd[bj][r];
+          const bool yslow = ((uint32_t)__double2hiint(yd) & 0x7ff00000u) == 0x7ff00000u;
+          const float *dp = &sd[r * cwp + sgm * kSegCols + lane];
+          float dd[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dd[k] = dp[32 * k];
+          float4 p[4];
+          bool kp[4];
+          points_of4_keep(Q, xd, yd, yslow || xslow, u0, a.border + row0 + r, dd, sure_lo, fast_span, p, kp);
+          uint32_t pos = unit_off[bj][r * n_seg + sgm];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pos = store_ranked_tight(out_f, pos, p[k], kp[k]);
+        }
+        g += kCW;
+      }
+      base += (uint32_t)n_seg;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_empty[bj]);
+      if (++bj == (uint32_t)B) bj = 0, ++use_j;
     }
   }
 }
@@ -1053,6 +1525,24 @@ cudaError_t launch_compact(K kernel, const ReprojArgs &a, int grid, cudaStream_t
 template <typename InT, int kMath>
 cudaError_t launch_typed(const ReprojArgs &a, bool vec, bool compact, int grid, int min_blocks, cudaStream_t s) {
   if (compact) {
+    if constexpr (kMath == kMathRect0 && sizeof(InT) == 4) {
+      if (a.pipe_stages > 0) {  // warp-specialised pipeline kernel
+        const size_t smem = (size_t)a.pipe_stages * a.band_rows * a.cw_pad * sizeof(float);
+        auto kern = reproject_compact_pipe_kernel<2, 8>;  // 320 threads, three CTAs per SM
+        int threads = 320;
+        switch (a.pipe_producers * 100 + a.pipe_consumers) {
+          case 108: kern = reproject_compact_pipe_kernel<1, 8>, threads = 288; break;
+          case 408: kern = reproject_compact_pipe_kernel<4, 8>, threads = 384; break;
+          case 212: kern = reproject_compact_pipe_kernel<2, 12>, threads = 448; break;  // two CTAs per SM
+          case 412: kern = reproject_compact_pipe_kernel<4, 12>, threads = 512; break;
+          default: break;
+        }
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, threads, smem, s>>>(a);
+        return cudaGetLastError();
+      }
+    }
     if constexpr (kMath == kMathRect0) {
       if (a.d_sure_bits != 0 && a.band_rows > 0) {  // band kernel
         const size_t smem = (size_t)a.band_rows * a.cw_pad * sizeof(float);
@@ -1258,7 +1748,34 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
       if (launches) *launches += 3;
       return cudaGetLastError();
     }
-    if (a.d_sure_bits != 0 && (L.compact_variant == 0 || L.compact_variant == 3)) {
+    if (a.d_sure_bits != 0 && L.in_is_f32 && vec && L.compact_variant == 5) {  // opt-in: measured slower than the band kernel
+      // pipeline kernel: R rows per tile, `stages` tiles resident per CTA; 8 consumer warps -> three CTAs per
+      // SM (~70 KB of stages each), 12 -> two CTAs per SM (~108 KB)
+      a.cw_pad = a.n_seg * kSegCols;
+      const size_t row_bytes = (size_t)a.cw_pad * sizeof(float);
+      const int consumers = L.pipe_consumers == 8 ? 8 : 12;
+      const int per_sm = consumers == 12 ? 2 : 3;
+      const size_t budget = (consumers == 12 ? 106 : 68) * 1024;
+      int stages = L.pipe_stages > 0 ? std::min(L.pipe_stages, kPipeMaxStages) : 6;
+      if (stages < 3) stages = 3;
+      while (stages > 3 && budget / (stages * row_bytes) < 1) --stages;
+      int r = (int)std::min<size_t>(budget / (stages * row_bytes), (size_t)kPipeMaxRows);
+      r = std::min(r, kPipeMaxUnits / a.n_seg);
+      if (L.rows_per_unit > 0) r = std::min(r, L.rows_per_unit);
+      if (r > (int)ch) r = (int)ch;
+      if (r >= 1) {
+        a.band_rows = r;
+        a.pipe_stages = stages;
+        a.pipe_consumers = consumers;
+        a.pipe_producers = (L.pipe_producers == 1 || L.pipe_producers == 2 || L.pipe_producers == 4) ? L.pipe_producers : 4;
+        if (consumers == 12 && a.pipe_producers == 1) a.pipe_producers = 2;
+        a.tiles_per_frame = (uint32_t)((ch + r - 1) / r);
+        const uint64_t total_t = (uint64_t)a.tiles_per_frame * L.n_frames;
+        if (total_t > 0xffffffffull) return cudaErrorInvalidValue;
+        grid = (int)std::min<uint64_t>(total_t, (uint64_t)L.sm_count * per_sm);
+      }
+    }
+    if (a.d_sure_bits != 0 && a.pipe_stages == 0 && (L.compact_variant == 0 || L.compact_variant == 3)) {
       // band geometry: R rows per CTA (<= ~46 KB of disparities, <= 512 units), split into row groups so that
       // (segments x groups) fills the 8 warps evenly
       a.cw_pad = a.n_seg * kSegCols;
@@ -1283,7 +1800,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
         grid = (int)total_b;
       }
     }
-    if (a.Q.rectified && !L.arith_fast && !L.force_generic && a.band_rows == 0) {
+    if (a.Q.rectified && !L.arith_fast && !L.force_generic && (a.band_rows == 0 || a.pipe_stages > 0)) {
       const int n = (int)(L.width + kSegCols > L.height ? L.width + kSegCols : L.height);
       rect_tables_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a.Q.q03, a.Q.q13, (int)L.width, (int)L.height, tabs,
                                                             tabs + L.width + kSegCols);
