@@ -82,7 +82,7 @@ struct d2pc_ctx {
   // tuning / test hooks
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0, median_variant = 0;
   bool force_scalar = false, force_generic = false;
-  int compact_variant = 0, exact_variant = 0, pipe_stages = 0, pipe_producers = 0, pipe_consumers = 0;
+  int compact_variant = 0, exact_variant = 0, pipe_stages = 0, pipe_producers = 0, pipe_consumers = 0, prefetch_dist = 0;
   std::vector<std::pair<uintptr_t, bool>> pin_cache;  // host pointer -> cudaHostAlloc'ed?
 };
 
@@ -243,6 +243,7 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
   L.pipe_stages = ctx->pipe_stages;
   L.pipe_producers = ctx->pipe_producers;
   L.pipe_consumers = ctx->pipe_consumers;
+  L.prefetch_dist = ctx->prefetch_dist;
   CU(ctx, launch_reproject(L, stream, &nl));
   ctx->launches += nl;
   return D2PC_OK;
@@ -562,6 +563,7 @@ int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value) {
   else if (k == "pipe_stages") ctx->pipe_stages = value;
   else if (k == "pipe_producers") ctx->pipe_producers = value;
   else if (k == "pipe_consumers") ctx->pipe_consumers = value;
+  else if (k == "prefetch_dist") ctx->prefetch_dist = value;
   else if (k == "median_ksize") {
     if (value < 1 || value > 15 || !(value & 1)) return D2PC_ERR_INVALID_ARG;
     ctx->cfg.median_ksize = value;

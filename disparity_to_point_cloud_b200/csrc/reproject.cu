@@ -52,6 +52,7 @@ struct ReprojArgs {
   const double *xtab, *ytab;  // (double)(float)(u + q03), (double)(float)(v + q13)
   uint32_t d_sure_bits;       // float bits of the smallest |d| whose point is certainly finite (rect0 compaction)
   int band_rows, cw_pad, band_groups, group_rows;  // band kernel geometry
+  int prefetch_dist;          // band kernel: L2 prefetch distance in tiles (0 = off)
   int pipe_stages;            // pipeline kernel: shared-memory stages (tiles in flight per CTA); 0 = not used
   int pipe_producers;         // pipeline kernel: producer warps per CTA (1, 2 or 4)
   int pipe_consumers;         // pipeline kernel: consumer warps per CTA (8: three CTAs per SM, 12: two)
@@ -1000,6 +1001,18 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
       for (int r = 0; r < rows_here; ++r)
         tma_load_1d(smem_u32(&sd[r * cwp]), src + (size_t)r * a.step, (uint32_t)cw4 * 4u, &bar_rows);
     }
+    if (threadIdx.x == 32 && a.prefetch_dist > 0) {
+      // pull the band that a CTA launched ~one wave later will need into L2, off everybody's critical path
+      const uint64_t t2 = (uint64_t)tile + (uint64_t)a.prefetch_dist;
+      if (t2 < (uint64_t)a.tiles_per_frame * (uint64_t)a.n_frames) {
+        const uint32_t f2 = (uint32_t)(t2 / a.tiles_per_frame);
+        const int row2 = (int)((uint32_t)t2 - f2 * a.tiles_per_frame) * R, rows2 = min(R, a.ch - row2);
+        const uint8_t *src2 = a.in + (size_t)f2 * a.frame_stride + (size_t)(a.border + row2) * a.step + (size_t)a.border * 4;
+        for (int r = 0; r < rows2; ++r)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src2 + (size_t)r * a.step), "r"((uint32_t)cw4 * 4u)
+                       : "memory");
+      }
+    }
     const int pad4 = (cwp - cw4) >> 2;  // float4 groups of padding per row
     for (int t = (int)threadIdx.x; t < pad4 * rows_here; t += kCThreads) {
       const int r = t / pad4, g4 = t - r * pad4;
@@ -1049,27 +1062,42 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
   const uint32_t sure_lo = a.d_sure_bits, sure_span = 0x7f800000u - a.d_sure_bits;
   // straight-line class of step 5: d_sure <= |d| < min(d_hi, inf) (d_hi: see reproject_exact_rectified)
   const uint32_t fast_span = max(min(Q.dhi_bits, 0x7f800000u), sure_lo) - sure_lo;
-  for (int r = 0; r < R; ++r)
-    for (int sgm = wic; sgm < n_seg; sgm += kCWarps) {
-      const float4 d4 = *reinterpret_cast<const float4 *>(&sd[r * cwp + sgm * kSegCols + 4 * lane]);
-      const uint32_t m0 = __float_as_uint(d4.x) & 0x7fffffffu, m1 = __float_as_uint(d4.y) & 0x7fffffffu;
-      const uint32_t m2 = __float_as_uint(d4.z) & 0x7fffffffu, m3 = __float_as_uint(d4.w) & 0x7fffffffu;
-      // sure class: d_sure <= |d| < inf
-      uint32_t cnt = ((m0 - sure_lo) < sure_span) + ((m1 - sure_lo) < sure_span) + ((m2 - sure_lo) < sure_span) +
-                     ((m3 - sure_lo) < sure_span);
-      // sliver class: 0 < |d| < d_sure -- decided exactly, rare
-      const bool s0 = (m0 - 1u) < (sure_lo - 1u), s1 = (m1 - 1u) < (sure_lo - 1u);
-      const bool s2 = (m2 - 1u) < (sure_lo - 1u), s3 = (m3 - 1u) < (sure_lo - 1u);
-      if (__builtin_expect(s0 || s1 || s2 || s3, 0)) {
-        const int u = a.border + sgm * kSegCols + 4 * lane, v = a.border + row0 + r;
-        if (s0) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 0, v, d4.x)) ? 1u : 0u;
-        if (s1) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 1, v, d4.y)) ? 1u : 0u;
-        if (s2) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 2, v, d4.z)) ? 1u : 0u;
-        if (s3) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 3, v, d4.w)) ? 1u : 0u;
+  // The band is a flat array of units (cw_pad = n_seg * 128, so unit u starts at float 128 * u).  A warp takes
+  // four consecutive units at a time; each lane counts its 4 pixels of every unit into one byte of a word and a
+  // single REDUX adds all four units at once (a unit has 128 pixels, so no byte can carry into the next).
+  for (int u0 = 4 * wic; u0 < n_units; u0 += 4 * kCWarps) {
+    uint32_t packed = 0;
+    bool rare = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (u0 + q < n_units) {
+        const float4 d4 = *reinterpret_cast<const float4 *>(&sd[(u0 + q) * kSegCols + 4 * lane]);
+        const uint32_t m0 = __float_as_uint(d4.x) & 0x7fffffffu, m1 = __float_as_uint(d4.y) & 0x7fffffffu;
+        const uint32_t m2 = __float_as_uint(d4.z) & 0x7fffffffu, m3 = __float_as_uint(d4.w) & 0x7fffffffu;
+        // sure class: d_sure <= |d| < inf
+        const uint32_t cq = ((m0 - sure_lo) < sure_span) + ((m1 - sure_lo) < sure_span) +
+                            ((m2 - sure_lo) < sure_span) + ((m3 - sure_lo) < sure_span);
+        rare |= min(min(m0 - 1u, m1 - 1u), min(m2 - 1u, m3 - 1u)) < sure_lo - 1u;  // sliver class 0 < |d| < d_sure
+        packed |= cq << (8 * q);
       }
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (lane == 0) unit_off[r * n_seg + sgm] = cnt;
     }
+    if (__builtin_expect(rare, 0)) {  // slivers are decided by the exact path
+#pragma unroll 1
+      for (int q = 0; q < 4 && u0 + q < n_units; ++q) {
+        const int r = (u0 + q) / n_seg, sgm = (u0 + q) - r * n_seg;
+        const float *px = &sd[(u0 + q) * kSegCols + 4 * lane];
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t m = __float_as_uint(px[e]) & 0x7fffffffu;
+          if ((m - 1u) < (sure_lo - 1u) &&
+              point_is_finite(reproject_exact_slow(Q.q, a.border + sgm * kSegCols + 4 * lane + e, a.border + row0 + r, px[e])))
+            packed += 1u << (8 * q);
+        }
+      }
+    }
+    packed = __reduce_add_sync(0xffffffffu, packed);
+    if (lane < 4 && u0 + lane < n_units) unit_off[u0 + lane] = (packed >> (8 * lane)) & 0xffu;
+  }
   __syncthreads();
   // ---- 3. exclusive scan of the unit counts (two entries per thread)
   uint32_t band_total;
@@ -1798,6 +1826,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
         const uint64_t total_b = (uint64_t)a.tiles_per_frame * L.n_frames;
         if (total_b > 0xffffffffull) return cudaErrorInvalidValue;
         grid = (int)total_b;
+        a.prefetch_dist = L.prefetch_dist < 0 ? 0 : (L.prefetch_dist > 0 ? L.prefetch_dist : L.sm_count);  // measured plateau: 100-300 tiles
       }
     }
     if (a.Q.rectified && !L.arith_fast && !L.force_generic && (a.band_rows == 0 || a.pipe_stages > 0)) {

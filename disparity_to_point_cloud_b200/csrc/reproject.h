@@ -51,6 +51,7 @@ struct ReprojectLaunch {
                                // 1 = park-then-compact, 2 = classify-first tiles, 3 = band, 5 = warp-specialised
                                // TMA pipeline (1-3, 5: single pass, decoupled look-back),
                                // 4 = two-pass count / scan / offset store (reads the disparity twice)
+  int prefetch_dist = 0;       // band kernel: L2 prefetch distance in tiles (0 = automatic, < 0 = off)
   int pipe_stages = 0;         // pipeline kernel: stages per CTA (0 = automatic)
   int pipe_producers = 0;      // pipeline kernel: producer warps per CTA (0 = automatic)
   int pipe_consumers = 0;      // pipeline kernel: consumer warps per CTA (0 = automatic, 8 or 12)

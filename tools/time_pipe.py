@@ -43,6 +43,9 @@ d[303, 103] = 1e-38
 want = oracle.filter_finite(oracle.disparity_cb_f32(d, q)).tobytes()
 ctx.set_filter_mode(1)
 for (var, pw, cw_, st, rows) in configs:
+    if var == 3:
+        ctx.set_tuning('prefetch_dist', pw)
+
     ctx.set_tuning("compact_variant", var)
     ctx.set_tuning("pipe_producers", pw)
     ctx.set_tuning("pipe_consumers", cw_)
@@ -61,6 +64,8 @@ for (w, h, f, kind) in [(1280, 720, 64, "s3"), (1280, 720, 64, "s2"), (3840, 216
     d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
     d_cnt = torch.zeros(f, dtype=torch.int32, device="cuda")
     for (var, pw, cw_, st, rows) in configs:
+        if var == 3:
+            ctx.set_tuning('prefetch_dist', pw)
         ctx.set_tuning("compact_variant", var)
         ctx.set_tuning("pipe_producers", pw)
         ctx.set_tuning("pipe_consumers", cw_)
