@@ -1192,8 +1192,16 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
       bool kp[4];
       points_of4_keep(Q, xd, yd, yslow || xslow != 0u, u0, a.border + row0 + r, dd, sure_lo, fast_span, p, kp);
       uint32_t pos = unit_off[r * n_seg + sgm];
+      if (__all_sync(0xffffffffu, kp[0] && kp[1] && kp[2] && kp[3])) {
+        // the whole unit survives (the common case): four contiguous 512-byte bursts, no ranking (POPC shares the
+        // quarter-rate XU pipe with the float64 conversions, which is this kernel's busiest pipe)
+        float4 *o = out_f + pos + lane;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pos = store_ranked_tight(out_f, pos, p[k], kp[k]);
+        for (int k = 0; k < 4; ++k) __stcs(o + 32 * k, p[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pos = store_ranked_tight(out_f, pos, p[k], kp[k]);
+      }
     }
   }
 }
