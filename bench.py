@@ -377,6 +377,12 @@ def run_extras(ctx, stream, torch, d2pc, synth):
     by = 4 * n * f + 16 * kept
     out["config3_crop_finite_kernel"] = {"Mpixel/s": f * w * h / s / 1e6, "GB/s": by / s / 1e9,
                                          "frac_of_hbm_peak": by / s / 1e9 / peak, "kept_fraction": kept / (n * f)}
+    # the literal any-Q exact path on the same batch (what a non-rectified Q would take)
+    ctx.set_tuning("force_generic", 1)
+    s = _time_launches(torch, stream, lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4,
+                                                                       d_out.data_ptr(), n * 16), 20)
+    ctx.set_tuning("force_generic", 0)
+    out["config3_generic_q_exact_kernel"] = {"Mpixel/s": f * w * h / s / 1e6, "frac_of_hbm_peak": 20 * n * f / s / 1e9 / peak}
     # FAST arithmetic on the same batch
     ctx.set_arith_mode(d2pc.ARITH_FAST)
     s = _time_launches(torch, stream, lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4,

@@ -14,7 +14,8 @@
 //     anything else throws std::invalid_argument (the reference would throw cv_bridge::Exception for encodings
 //     it can not convert, src/disparity_to_point_cloud.cpp:50).
 //   * the nine printf progress lines per frame (cpp:47-91) are dropped; `verbose` prints "Cloud size: N".
-//   * the six debug publishers of the fusion node (colourised views) are not produced.
+//   * the six debug views of the fusion node are computed only while somebody subscribes to them (a roscpp
+//     publisher without subscribers does not serialise either).
 #pragma once
 #include <algorithm>
 #include <cstdio>
@@ -91,6 +92,10 @@ class Bus {
       for (auto &s : it->second) s.cb(msg);
   }
   const std::vector<Advertised> &advertised() const { return advertised_; }
+  bool has_subscribers(const std::string &resolved_topic) const {  // ros::Publisher::getNumSubscribers() > 0
+    auto it = image_subs_.find(resolved_topic);
+    return it != image_subs_.end() && !it->second.empty();
+  }
 
   // Reads <remap from= to=/> and <param name= value=/> out of a roslaunch file (launch/*.launch).
   bool load_launch_file(const std::string &path) {
@@ -254,6 +259,61 @@ class DepthMapFusion {
     have = true;
   }
 
+  // ---- the debug views (depth_map_fusion.hpp:106-117, src/depth_map_fusion.cpp:275-302)
+  enum { GRAY_SCALE = -1, RAINBOW_WITH_BLACK = -2 };  // depth_map_fusion.hpp:66-67
+  std::string cropped_depth_1_topic_, cropped_depth_2_topic_, cropped_score_1_topic_, cropped_score_2_topic_,
+      combined_topic_, grad_topic_;
+
+  // publishWithColor (cpp:275-302): GRAY_SCALE publishes the mat as mono8, RAINBOW_WITH_BLACK runs colorizeDepth
+  // (cpp:304-358, on the GPU: d2pc_colorize_depth) and labels the result "rgb8" as the reference does.
+  void publishWithColor(const sensor_msgs::ImageConstPtr &msg, const uint8_t *mat, uint32_t w, uint32_t h,
+                        uint32_t step, const std::string &topic, int colormap) {
+    if (!nh_.has_subscribers(topic)) return;
+    auto out = std::make_shared<sensor_msgs::Image>();
+    out->header = msg->header;
+    out->height = h;
+    out->width = w;
+    out->is_bigendian = 0;
+    if (colormap == GRAY_SCALE) {
+      out->encoding = "mono8";
+      out->step = w;
+      out->data.resize(static_cast<size_t>(w) * h);
+      for (uint32_t y = 0; y < h; ++y)
+        std::copy_n(mat + static_cast<size_t>(y) * step, w, out->data.data() + static_cast<size_t>(y) * w);
+    } else {
+      d2pc_image rgb;
+      d2pc_b200::check(d2pc_colorize_depth(ctx_, mat, w, h, step, &rgb), "d2pc_colorize_depth", ctx_);
+      out->encoding = "rgb8";
+      out->step = 3 * w;
+      out->data.resize(static_cast<size_t>(3) * w * h);
+      for (uint32_t y = 0; y < h; ++y)
+        std::copy_n(rgb.data + static_cast<size_t>(y) * rgb.step, 3 * w, out->data.data() + static_cast<size_t>(y) * 3 * w);
+    }
+    nh_.publish(topic, sensor_msgs::ImageConstPtr(out));
+  }
+
+  // cropToSquare(image, +-offset) as a dense n x n copy, for the debug views only (the fusion kernel itself never
+  // materialises the crop).  which == 2 also applies rotateMat (cpp:268-273): rot(r, c) = src(H-1-c, r).
+  std::vector<uint8_t> cropped_view(const sensor_msgs::Image &m, int which, uint32_t &n) {
+    int r1[4], r2[4], rc[4], dims[3];
+    d2pc_b200::check(d2pc_fuse_geometry(ctx_, m.width, m.height, r1, r2, rc, dims), "d2pc_fuse_geometry");
+    n = static_cast<uint32_t>(dims[0]);
+    const int *r = which == 1 ? r1 : r2;
+    std::vector<uint8_t> v(static_cast<size_t>(n) * n);
+    for (uint32_t i = 0; i < n; ++i)
+      for (uint32_t j = 0; j < n; ++j)
+        v[static_cast<size_t>(i) * n + j] =
+            which == 1 ? m.data[static_cast<size_t>(r[1] + i) * m.step + r[0] + j]
+                       : m.data[static_cast<size_t>(m.height - 1 - (r[0] + j)) * m.step + r[1] + i];
+    return v;
+  }
+  void publish_cropped_depth(const sensor_msgs::ImageConstPtr &msg, int which, const std::string &topic) {
+    if (!nh_.has_subscribers(topic)) return;
+    uint32_t n = 0;
+    const std::vector<uint8_t> v = cropped_view(*msg, which, n);
+    publishWithColor(msg, v.data(), n, n, n, topic, RAINBOW_WITH_BLACK);
+  }
+
  public:
   int offset_x_ = 0;
   int offset_y_ = 0;
@@ -265,8 +325,14 @@ class DepthMapFusion {
     nh_.subscribe_image("/disparity_2", 1, [this](const sensor_msgs::ImageConstPtr &m) { DisparityCb2(m); });
     nh_.subscribe_image("/matching_score_1", 1, [this](const sensor_msgs::ImageConstPtr &m) { MatchingScoreCb1(m); });
     nh_.subscribe_image("/matching_score_2", 1, [this](const sensor_msgs::ImageConstPtr &m) { MatchingScoreCb2(m); });
-    // :106-117 (only the fused map is produced; the six debug views are visualisation)
+    // :106-117
+    cropped_depth_1_topic_ = nh_.advertise("/cropped_depth_1", 5);
+    cropped_depth_2_topic_ = nh_.advertise("/cropped_depth_2", 5);
+    cropped_score_1_topic_ = nh_.advertise("/cropped_score_1", 5);
+    cropped_score_2_topic_ = nh_.advertise("/cropped_score_2", 5);
     fused_topic_ = nh_.advertise("/fused_depth_map", 5);
+    combined_topic_ = nh_.advertise("/combined_score", 5);
+    grad_topic_ = nh_.advertise("/gradient", 5);
     // :119-124
     if (!nh_.get_param("offset_x", offset_x_)) std::fprintf(stderr, "[ WARN] Failed to load parameter offset_x\n");
     if (!nh_.get_param("offset_y", offset_y_)) std::fprintf(stderr, "[ WARN] Failed to load parameter offset_y\n");
@@ -280,16 +346,22 @@ class DepthMapFusion {
   DepthMapFusion(const DepthMapFusion &) = delete;
   DepthMapFusion &operator=(const DepthMapFusion &) = delete;
 
-  void DisparityCb1(const sensor_msgs::ImageConstPtr &msg) { cache(msg, depth_1_, have_d1_); }  // cpp:46-52
-  void DisparityCb2(const sensor_msgs::ImageConstPtr &msg) {                                  // cpp:54-62
+  void DisparityCb1(const sensor_msgs::ImageConstPtr &msg) {  // cpp:46-52
+    cache(msg, depth_1_, have_d1_);
+    publish_cropped_depth(msg, 1, cropped_depth_1_topic_);
+  }
+  void DisparityCb2(const sensor_msgs::ImageConstPtr &msg) {  // cpp:54-62
     cache(msg, depth_2_, have_d2_);
+    publish_cropped_depth(msg, 2, cropped_depth_2_topic_);
     publishFusedDepthMap(msg);
   }
   void MatchingScoreCb1(const sensor_msgs::ImageConstPtr &msg) {  // cpp:64-80
     preprocess(msg, 1, cropped_score_1_, score_n_1_, have_s1_);
+    publishWithColor(msg, cropped_score_1_.data(), score_n_1_, score_n_1_, score_n_1_, cropped_score_1_topic_, GRAY_SCALE);
   }
   void MatchingScoreCb2(const sensor_msgs::ImageConstPtr &msg) {  // cpp:82-99
     preprocess(msg, 2, cropped_score_2_, score_n_2_, have_s2_);
+    publishWithColor(msg, cropped_score_2_.data(), score_n_2_, score_n_2_, score_n_2_, cropped_score_2_topic_, GRAY_SCALE);
   }
 
   // src/depth_map_fusion.cpp:103-136
@@ -318,6 +390,8 @@ class DepthMapFusion {
     for (int i = 0; i < dims[0]; ++i)
       std::copy_n(combined.data + static_cast<size_t>(i) * combined.step, dims[0],
                   cropped_score_1_.data() + static_cast<size_t>(i) * dims[0]);
+    // :126-127 the combined score, :132 the colourised fused map (d2pc_colorize_depth reuses the context's
+    // output buffers, so the fused pixels are copied out first)
     auto out = std::make_shared<sensor_msgs::Image>();  // disparity->toImageMsg(fused_image), :134-135
     out->header = msg->header;
     out->height = fused.height;
@@ -328,6 +402,8 @@ class DepthMapFusion {
     out->data.resize(static_cast<size_t>(fused.width) * fused.height);
     for (uint32_t y = 0; y < fused.height; ++y)
       std::copy_n(fused.data + static_cast<size_t>(y) * fused.step, fused.width, out->data.data() + static_cast<size_t>(y) * fused.width);
+    publishWithColor(msg, cropped_score_1_.data(), dims[0], dims[0], dims[0], combined_topic_, GRAY_SCALE);
+    publishWithColor(msg, out->data.data(), out->width, out->height, out->step, grad_topic_, RAINBOW_WITH_BLACK);
     nh_.publish(fused_topic_, sensor_msgs::ImageConstPtr(out));  // :136
   }
 };

@@ -21,10 +21,12 @@ def harness():
 
 
 def image_msg(img, sec, nsec, seq=0, frame_id="camera"):
-    h, w = img.shape
+    """sensor_msgs/Image on the ROS1 wire; (H, W) is mono8, (H, W, 3) is what the reference labels rgb8."""
+    h, w = img.shape[:2]
     fid = frame_id.encode()
+    enc, step = (b"mono8", w) if img.ndim == 2 else (b"rgb8", 3 * w)
     return (struct.pack("<III", seq, sec, nsec) + struct.pack("<I", len(fid)) + fid + struct.pack("<II", h, w) +
-            struct.pack("<I", 5) + b"mono8" + struct.pack("<BI", 0, w) + struct.pack("<I", w * h) + img.tobytes())
+            struct.pack("<I", len(enc)) + enc + struct.pack("<BI", 0, step) + struct.pack("<I", step * h) + img.tobytes())
 
 
 def test_wire_selftest(harness, tmp_path):
@@ -69,9 +71,10 @@ def test_fusion_node_then_node1_config5(harness, tmp_path):
         p = tmp_path / f"{name}.raw"
         p.write_bytes(a.tobytes())
         paths.append(str(p))
-    fused_bin, cloud_bin = tmp_path / "fused.bin", tmp_path / "cloud.bin"
+    fused_bin, cloud_bin, dbg = tmp_path / "fused.bin", tmp_path / "cloud.bin", tmp_path / "debug"
+    dbg.mkdir()
     subprocess.run([harness, "fusion", os.path.join(ROOT, "launch", "depth_map_fusion.launch"), str(w), str(h)] + paths +
-                   [str(fused_bin), str(cloud_bin)], check=True)
+                   [str(fused_bin), str(cloud_bin), str(dbg)], check=True)
     # MatchingScoreCb1/2 preprocess the scores (src/depth_map_fusion.cpp:64-99) before they are cached
     _, r1 = oracle.crop_to_square(w, h, -7, 15, 15)
     _, r2 = oracle.crop_to_square(h, w, 7, -15, 15)
@@ -81,8 +84,19 @@ def test_fusion_node_then_node1_config5(harness, tmp_path):
     c1[r1[1]:r1[1] + r1[2], r1[0]:r1[0] + r1[2]] = p1
     rot = np.zeros((w, h), np.uint8)
     rot[r2[1]:r2[1] + r2[2], r2[0]:r2[0] + r2[2]] = p2
-    fused, _ = oracle.fuse(d1, d2, c1, np.ascontiguousarray(np.rot90(rot, 1)), -7, 15)
+    fused, combined = oracle.fuse(d1, d2, c1, np.ascontiguousarray(np.rot90(rot, 1)), -7, 15)
     assert fused.shape == (665, 665)
+    # the six debug topics (depth_map_fusion.hpp:106-117; publishWithColor, src/depth_map_fusion.cpp:275-302), each
+    # with the header of the message whose callback published it
+    crop1 = d1[r1[1]:r1[1] + r1[2], r1[0]:r1[0] + r1[2]]
+    crop2 = oracle.rotate_cw(d2)[r2[1]:r2[1] + r2[2], r2[0]:r2[0] + r2[2]]
+    want_dbg = {"cropped_depth_1": image_msg(oracle.colorize_depth(crop1), 1, 0),
+                "cropped_depth_2": image_msg(oracle.colorize_depth(crop2), 2, 500),
+                "cropped_score_1": image_msg(p1, 1, 0), "cropped_score_2": image_msg(p2, 1, 0),
+                "combined_score": image_msg(np.ascontiguousarray(combined), 2, 500),
+                "gradient": image_msg(oracle.colorize_depth(fused), 2, 500)}
+    for name, want_bytes in want_dbg.items():
+        assert (dbg / f"{name}.bin").read_bytes() == want_bytes, name
     assert fused_bin.read_bytes() == image_msg(fused, 2, 500)          # header of message 2 (:134-135)
     want = oracle.serialize_pointcloud2(oracle.disparity_cb_mono8(fused, q), seq=0, sec=2, nsec=500)
     assert cloud_bin.read_bytes() == want

@@ -5,16 +5,18 @@
 //   d2pc_offline node1  <launch file> <w> <h> <in.raw> <out.bin> [sec nsec]
 //       BASELINE config 1/2 shape: one mono8 frame published on the node's (remapped) input topic; the
 //       PointCloud2 received on the (remapped) output topic is written in ROS1 wire format.
-//   d2pc_offline fusion <fusion launch> <w> <h> <d1.raw> <d2.raw> <s1.raw> <s2.raw> <fused.bin> [<cloud.bin>]
+//   d2pc_offline fusion <fusion launch> <w> <h> <d1.raw> <d2.raw> <s1.raw> <s2.raw> <fused.bin> [<cloud.bin> [<debug dir>]]
 //       BASELINE config 5 shape: four mono8 frames into DepthMapFusion; the fused Image is written, and when
 //       <cloud.bin> is given it is also fed to a Disparity2PCloud node whose /disparity is remapped to
-//       /fused_depth_map.
+//       /fused_depth_map.  With <debug dir> the six debug topics are subscribed too and the last message of
+//       each is written there in wire format (cropped_depth_1.bin, ..., gradient.bin).
 //
 // It touches the GPU only through the C ABI (libd2pc_b200.so).
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -99,6 +101,12 @@ int main(int argc, char **argv) {
         node1.reset(new d2pc::Disparity2PCloud(*bus1));
         bus1->subscribe_cloud("/point_cloud", 1, [&](const sm::PointCloud2 &c) { cloud_bytes = ros_lite::serialize(c); });
       }
+      std::map<std::string, std::vector<uint8_t>> debug;
+      if (argc > 11)
+        for (const char *t : {"cropped_depth_1", "cropped_depth_2", "cropped_score_1", "cropped_score_2", "combined_score",
+                              "gradient"})
+          bus.subscribe_image(std::string("/") + t, 5,
+                              [&debug, t](const sm::ImageConstPtr &m) { debug[t] = ros_lite::serialize(*m); });
       // arrival order of the reference's typical use: scores, map 1, then map 2 triggers the fused publish
       bus.publish(bus.resolve("/matching_score_1"), make_image(read_file(argv[7], (size_t)w * h), w, h, 1, 0));
       bus.publish(bus.resolve("/matching_score_2"), make_image(read_file(argv[8], (size_t)w * h), w, h, 1, 0));
@@ -110,6 +118,10 @@ int main(int argc, char **argv) {
         bus1->publish("/fused_depth_map", fused);
         if (cloud_bytes.empty()) throw std::runtime_error("no point cloud was published");
         write_file(argv[10], cloud_bytes);
+      }
+      if (argc > 11) {
+        if (debug.size() != 6) throw std::runtime_error("a debug topic was not published");
+        for (const auto &kv : debug) write_file(std::string(argv[11]) + "/" + kv.first + ".bin", kv.second);
       }
       return 0;
     }
