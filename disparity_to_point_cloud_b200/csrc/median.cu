@@ -115,12 +115,16 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
       const uint8_t *row = src + (size_t)clampi(y + 1 + R, 0, a.height - 1) * a.src_step;
       const uint32_t na = hist_off(row[gx_a]);
       const uint32_t nb = (lane < K - 1) ? hist_off(row[gx_b]) : 0u;
-      // remove the oldest row
+      // remove the oldest row.  The K ring entries are read up front: the compiler can not move a ring load
+      // across a histogram store (both are shared memory), so reading them inside the update loop would put two
+      // dependent shared-memory latencies on every update instead of one.
+      uint32_t offs[K];
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) offs[dx] = ring[slot][lane + dx];
 #pragma unroll
       for (int dx = 0; dx < K; ++dx) {
-        const uint32_t off = ring[slot][lane + dx];
-        hb[off] = hb[off] - 1;
-        below -= (off < med_off) ? 1 : 0;
+        hb[offs[dx]] = hb[offs[dx]] - 1;
+        below -= (offs[dx] < med_off) ? 1 : 0;
       }
       __syncwarp();
       ring[slot][lane] = (uint16_t)na;
@@ -128,10 +132,11 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
       __syncwarp();
       // add the new row
 #pragma unroll
+      for (int dx = 0; dx < K; ++dx) offs[dx] = ring[slot][lane + dx];
+#pragma unroll
       for (int dx = 0; dx < K; ++dx) {
-        const uint32_t off = ring[slot][lane + dx];
-        hb[off] = hb[off] + 1;
-        below += (off < med_off) ? 1 : 0;
+        hb[offs[dx]] = hb[offs[dx]] + 1;
+        below += (offs[dx] < med_off) ? 1 : 0;
       }
       slot = (slot + 1 == K) ? 0 : slot + 1;
       // re-centre: invariant below <= kRank < below + hist[med]
