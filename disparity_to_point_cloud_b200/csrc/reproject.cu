@@ -1840,6 +1840,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
       r_max = std::min(r_max, kBandMaxUnits / a.n_seg);
       if (r_max < 1 && row_bytes <= 200 * 1024 && a.n_seg <= kBandMaxUnits) r_max = 1;
       if (r_max > (int)ch) r_max = (int)ch;
+      if (L.rows_per_unit > 0 && L.rows_per_unit < r_max) r_max = L.rows_per_unit;  // tuning knob
       double best = -1.0;
       for (int r = r_max; r >= 1 && r >= r_max - 3; --r)
         for (int g = 1; g <= r; ++g) {
