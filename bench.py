@@ -217,7 +217,7 @@ def run_ours(args):
     ring = min(RING, max(frames_per_step, 1))
     launches_per_step = (frames_per_step + ring - 1) // ring
 
-    ctx = d2pc.Context(device=local, n_slots=3)
+    ctx = d2pc.Context(device=local, n_slots=args.slots)
     stream = torch.cuda.ExternalStream(ctx.compute_stream(), device=torch.device("cuda", local))
 
     # ---- resident inputs: RING distinct S3 frames (seeded per rank so ranks do not share data)
@@ -457,6 +457,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP, help="frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=0, help="frames timed end to end (0 = one full step)")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--slots", type=int, default=3, help="pipeline slots per GPU of the end-to-end path")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --frames per GPU per step; strong: --frames in total, sharded i mod G")
     args = ap.parse_args()
