@@ -40,6 +40,13 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v,
 // monotonic in `bin`, so window pixels are kept in the ring already transformed and compared in this domain.
 __device__ __forceinline__ uint32_t hist_off(uint32_t bin) { return ((bin >> 2) << 7) | (bin & 3u); }
 
+// below += delta when off < med_off, as exactly two instructions (compare, predicated add); the compiler's own
+// rendering of `below += (off < med_off) ? delta : 0` is three (compare, add into a temporary, predicated move).
+template <int kDelta>
+__device__ __forceinline__ void bump_if_below(int &below, uint32_t off, uint32_t med_off) {
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.s32 %0, %0, %3;\n\t}" : "+r"(below) : "r"(off), "r"(med_off), "n"(kDelta));
+}
+
 template <int K>
 __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_constant__ MedianArgs a) {
   constexpr int R = K / 2;
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
 #pragma unroll
       for (int dx = 0; dx < K; ++dx) {
         hb[offs[dx]] = hb[offs[dx]] - 1;
-        below -= (offs[dx] < med_off) ? 1 : 0;
+        bump_if_below<-1>(below, offs[dx], med_off);
       }
       __syncwarp();
       ring[slot][lane] = (uint16_t)na;
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
 #pragma unroll
       for (int dx = 0; dx < K; ++dx) {
         hb[offs[dx]] = hb[offs[dx]] + 1;
-        below += (offs[dx] < med_off) ? 1 : 0;
+        bump_if_below<1>(below, offs[dx], med_off);
       }
       slot = (slot + 1 == K) ? 0 : slot + 1;
       // re-centre: invariant below <= kRank < below + hist[med]
