@@ -362,3 +362,63 @@ def test_full_size_compaction_4k(ctx, variant):
         ctx.set_tuning("compact_variant", 0)
     assert got.size == want.size == 16 * int(np.count_nonzero(d[40:-40, 40:-40]))
     assert_same_bits(got, want, f"4K compaction (variant {variant})")
+
+
+# ---- BASELINE.json configs at their full sizes --------------------------------------------------------------
+def test_config3_full_batch_1280x720x64(ctx):
+    """configs[2]: a resident batch of 64 1280x720 float frames through one launch, every frame bit-exact against
+    the oracle, in CROP and in CROP_FINITE mode (count, order and bits)."""
+    import torch
+    import disparity_to_point_cloud_b200 as d2pc
+    ctx.set_q(_default_q())
+    f, h, w = 64, 720, 1280
+    base = synth.s3_float(h, w, 3)
+    frames = np.stack([np.roll(base, 17 * i, axis=1) for i in range(f)])
+    frames[5, 100:140, 300:900] = 0.0
+    n = oracle.n_points(w, h)
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = torch.zeros((f, n * 16), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(f, dtype=torch.int32, device="cuda")
+    ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, h * w * 4, d_out.data_ptr(), n * 16)
+    ctx.sync()
+    got = d_out.cpu().numpy()
+    want = [oracle.disparity_cb_f32(frames[i], _default_q()) for i in range(f)]
+    for i in range(f):
+        assert_same_bits(got[i], want[i], f"frame {i}")
+    ctx.set_filter_mode(d2pc.FILTER_CROP_FINITE)
+    try:
+        d_out.zero_()
+        ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, h * w * 4, d_out.data_ptr(), n * 16, d_cnt.data_ptr())
+        ctx.sync()
+    finally:
+        ctx.set_filter_mode(d2pc.FILTER_CROP)
+    got, cnt = d_out.cpu().numpy(), d_cnt.cpu().numpy()
+    for i in range(f):
+        wf = oracle.filter_finite(want[i])
+        assert cnt[i] == wf.size // 16
+        assert_same_bits(got[i, :wf.size], wf, f"compacted frame {i}")
+
+
+def test_config4_ring_of_4k_frames_1024(ctx):
+    """configs[3] as bench.py runs it: 1024 3840x2160 frames streamed through a ring of 16 device slots (64
+    launches).  The 16 distinct frames are checked bit for bit against the oracle after the last launch, and the
+    ring is idempotent: every pass writes the same bytes (checksum of checksums over the passes)."""
+    import torch
+    ctx.set_q(_default_q())
+    ring, h, w = 16, 2160, 3840
+    base = synth.s3_float(h, w, 1000)
+    frames = np.stack([np.roll(base, 131 * i + 7, axis=1) for i in range(ring)])
+    n = oracle.n_points(w, h)
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = torch.zeros((ring, n * 16), dtype=torch.uint8, device="cuda")
+    sums = []
+    for launch in range(1024 // ring):
+        ctx.reproject_f32_device(d_in.data_ptr(), ring, w, h, w * 4, h * w * 4, d_out.data_ptr(), n * 16)
+        if launch in (0, 31, 63):
+            ctx.sync()
+            sums.append(int(d_out.view(torch.int32).sum(dtype=torch.int64).item()))
+    ctx.sync()
+    assert sums[0] == sums[1] == sums[2]
+    got = d_out.cpu().numpy()
+    for i in range(ring):
+        assert_same_bits(got[i], oracle.disparity_cb_f32(frames[i], _default_q()), f"ring slot {i}")
