@@ -47,11 +47,12 @@ struct ReprojectLaunch {
   bool force_scalar = false;   // exercise the unaligned load path
   bool force_generic = false;  // exercise the generic-Q exact path on a rectified Q
   int exact_variant = 0;       // rectified exact quotients: 0 = guarded multiply (7 FP64 ops), 1 = Markstein (15)
-  int compact_variant = 0;     // CROP_FINITE kernel: 0 = automatic (pipeline / band where Q allows, else park),
+  int compact_variant = 0;     // CROP_FINITE kernel: 0 = automatic (band where Q allows, else park),
                                // 1 = park-then-compact, 2 = classify-first tiles, 3 = band, 5 = warp-specialised
                                // TMA pipeline (1-3, 5: single pass, decoupled look-back),
                                // 4 = two-pass count / scan / offset store (reads the disparity twice)
-  int prefetch_dist = 0;       // band kernel: L2 prefetch distance in tiles (0 = automatic, < 0 = off)
+  int prefetch_dist = 0;       // L2 prefetch distance: CROP kernel in work units, band kernel in tiles
+                               // (0 = automatic, < 0 = off)
   int pipe_stages = 0;         // pipeline kernel: stages per CTA (0 = automatic)
   int pipe_producers = 0;      // pipeline kernel: producer warps per CTA (0 = automatic)
   int pipe_consumers = 0;      // pipeline kernel: consumer warps per CTA (0 = automatic, 8 or 12)
