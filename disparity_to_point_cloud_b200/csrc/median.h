@@ -16,7 +16,8 @@ struct MedianLaunch {
   int ksize = 11;
   int sm_count = 148;
   int strip_rows = 0;  // 0 = automatic
-  int variant = 0;     // 0 = per-thread window histogram (Huang), 1 = column histograms
+  int variant = 0;     // 0 = per-thread window histogram (Huang; a selection network for ksize 3),
+                       // 1 = column histograms, 2 = window histogram for every ksize
 };
 
 cudaError_t launch_median_u8(const MedianLaunch &L, cudaStream_t stream, int *launches);

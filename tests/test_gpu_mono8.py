@@ -48,11 +48,12 @@ def test_mono8_4k(ctx, q):
     assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, q), "4K mono8")
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("ksize", [3, 5, 7, 9, 11, 13, 15])
 @pytest.mark.parametrize("w,h", [(96, 64), (7, 5), (333, 222), (32, 300), (1, 40), (40, 1)])
 def test_median_kernel_full_frame(ctx, ksize, w, h, variant):
-    """variant 0: per-thread window histogram; variant 1: column histograms."""
+    """variant 0: per-thread window histogram (19-exchange selection network for ksize 3); 1: column histograms;
+    2: window histogram for every ksize."""
     import torch
     ctx.set_tuning("median_variant", variant)
     img = synth.s1_uniform(h, w, 14 + ksize)
