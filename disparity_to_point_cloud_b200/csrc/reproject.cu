@@ -7,19 +7,22 @@
 // and, for the mono8 entry, Mat::convertTo(CV_32FC1, 1/8)     :60-61.
 //
 // CROP kernel (reference-exact filter: output offsets are closed form)
-//   work unit = 128 crop columns x RB crop rows, one warp per unit, grid-stride.
+//   work unit = 128 crop columns x RB crop rows, one warp per unit, one unit per warp (the CTA scheduler balances).
 //   Per row: each lane issues one 16-byte streaming load (4 disparities), the
 //   warp transposes through 512 B of shared memory so that lane L then owns
 //   pixels L, L+32, L+64, L+96 -- which makes every one of the four 16-byte
 //   point stores of the warp a contiguous 512-byte burst.  Column constants
 //   (X) live in registers for the whole unit, row constants (Y) are computed
 //   by one lane each and broadcast by shuffle; Q sits in the kernel parameter
-//   (constant) bank.
+//   (constant) bank.  Each warp prefetches into L2 (cp.async.bulk.prefetch.L2)
+//   the unit a warp launched a fraction of a wave later will read.
 //
-// CROP_FINITE kernel (extension: drop non-finite points, keep row-major order)
-//   single-pass chained scan with decoupled look-back: warp ballot/popc ->
-//   block scan -> 64-bit {epoch,flag,value} tile descriptors -> compacted tile
-//   staged in shared memory -> coalesced 16-byte stores.
+// CROP_FINITE kernels (extension: drop non-finite points, keep row-major order)
+//   band kernel (default for the stereoRectify form of Q): a CTA owns whole crop rows; TMA bulk row loads,
+//   survivors counted from the disparity alone (four units per REDUX), block scan, ONE decoupled look-back per
+//   band over 64-bit {epoch,flag,value} descriptors, survivors reprojected and stored at offset + ballot rank.
+//   pipeline kernel (opt-in): the same as persistent warp-specialised CTAs (TMA producers / mbarriers).
+//   park / classify-first tile kernels (any Q, FAST mode) and a two-pass count / scan / store variant.
 #include "reproject.h"
 
 #include <algorithm>
