@@ -318,6 +318,7 @@ def test_device_batch_compaction(ctx):
                 want = oracle.filter_finite(oracle.disparity_cb_f32(frames[i], _default_q()))
                 assert cnt[i] == want.size // 16
                 assert_same_bits(got[i, :want.size], want, f"frame {i} (variant {variant}, stages {stages})")
+                assert not got[i, want.size:].any(), "a compaction kernel wrote past the frame's last survivor"
     finally:
         ctx.set_filter_mode(d2pc.FILTER_CROP)
         ctx.set_tuning("compact_variant", 0)

@@ -15,7 +15,7 @@ with d2pc.Context(offset_x=-7, offset_y=15) as ctx:
     ctx.process_f32(d)
     ctx.process_f32(d[:, 3:300])              # scalar-load path
     ctx.process_mono8(img)
-    for variant in (0, 1, 2, 4):
+    for variant in (0, 1, 2, 3, 4, 5):
         ctx.set_tuning("compact_variant", variant)
         ctx.set_filter_mode(1)
         ctx.process_f32(d)
