@@ -42,6 +42,26 @@ struct Src {  // a mono8 image, optionally viewed through rotateMat (rot(r, c) =
   }
 };
 
+// Score 2 is read through rotateMat: walking along a row of the rotated image walks down a column of the stored
+// frame, so a row filter over it would make 13 uncoalesced reads per output.  The (n + 12)^2 neighbourhood of the
+// crop (reflect-101 at the frame edge, as the non-isolated ROI sees it) is therefore materialised once, through a
+// 32 x 32 shared-memory tile: reads run along the stored rows, writes along the rows of the rotated view.
+__global__ void __launch_bounds__(256) rotcrop_kernel(Src s, int x0, int y0, int m, uint8_t *out) {
+  __shared__ uint8_t tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int xx = blockIdx.x * 32 + ty + 8 * j, yy = blockIdx.y * 32 + tx;
+    if (xx < m && yy < m) tile[ty + 8 * j][tx] = (uint8_t)s.at(reflect101(x0 + xx, s.cols()), reflect101(y0 + yy, s.rows()));
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int xx = blockIdx.x * 32 + tx, yy = blockIdx.y * 32 + ty + 8 * j;
+    if (xx < m && yy < m) out[(size_t)yy * m + xx] = tile[tx][ty + 8 * j];
+  }
+}
+
 // rows pass of the fixed-point Gaussian: out16[(yy) * ow + x], yy in [0, oh + 2r), source row y0 + yy - r
 template <int KS>
 __global__ void gauss_rows_kernel(Src s, int x0, int y0, int ow, int oh, uint16_t *out16) {
@@ -145,14 +165,25 @@ cudaError_t launch_score_preprocess(const ScoreLaunch &L, cudaStream_t stream, i
   }
   const dim3 blk(128);
   const dim3 g13((n + 127) / 128, n + 12), g21((n + 127) / 128, n + 20), gn((n + 127) / 128, n);
-  gauss_rows_kernel<13><<<g13, blk, 0, stream>>>(s, L.rect[0], L.rect[1], n, n, L.rows16);
+  int n_launch = 6;
+  if (L.rotated && (size_t)(n + 12) * (n + 12) <= (size_t)n * n * 4) {
+    // (the float scratch is free until the Sobel pass)
+    uint8_t *roi = reinterpret_cast<uint8_t *>(L.f32);
+    const int m = n + 12;
+    rotcrop_kernel<<<dim3((m + 31) / 32, (m + 31) / 32), dim3(32, 8), 0, stream>>>(s, L.rect[0] - 6, L.rect[1] - 6, m, roi);
+    Src r{roi, (size_t)m, m, m, false};
+    gauss_rows_kernel<13><<<g13, blk, 0, stream>>>(r, 6, 6, n, n, L.rows16);
+    n_launch = 7;
+  } else {
+    gauss_rows_kernel<13><<<g13, blk, 0, stream>>>(s, L.rect[0], L.rect[1], n, n, L.rows16);
+  }
   gauss_cols_kernel<13, false><<<gn, blk, 0, stream>>>(L.rows16, n, n, s, 0, 0, L.tmp8a);
   sobel_rows_kernel<<<gn, blk, 0, stream>>>(L.tmp8a, n, L.rotated, K, L.f32);
   sobel_cols_thresh_kernel<<<gn, blk, 0, stream>>>(L.f32, n, L.rotated, K, L.tmp8b);
   Src e{L.tmp8b, (size_t)n, n, n, false};
   gauss_rows_kernel<21><<<g21, blk, 0, stream>>>(e, 0, 0, n, n, L.rows16);
   gauss_cols_kernel<21, true><<<gn, blk, 0, stream>>>(L.rows16, n, n, s, L.rect[0], L.rect[1], L.out);
-  if (launches) *launches = 6;
+  if (launches) *launches = n_launch;
   return cudaGetLastError();
 }
 
