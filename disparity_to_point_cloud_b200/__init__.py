@@ -258,21 +258,22 @@ class Context:
             a = np.ascontiguousarray(a, dtype=dtype)
         return a
 
-    def process_mono8(self, img) -> np.ndarray:
+    def process_mono8(self, img, copy: bool = True) -> np.ndarray:
+        """copy=False returns a view of the library-owned pinned buffer (valid until the next call)."""
         a = self._frame(img, np.uint8)
         cl = Cloud()
         self._check(lib().d2pc_process_mono8(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0],
                                              C.byref(cl)), "d2pc_process_mono8")
         self.last_cloud = cl
-        return cl.bytes_view().copy()
+        return cl.bytes_view().copy() if copy else cl.bytes_view()
 
-    def process_f32(self, disp) -> np.ndarray:
+    def process_f32(self, disp, copy: bool = True) -> np.ndarray:
         a = self._frame(disp, np.float32)
         cl = Cloud()
         self._check(lib().d2pc_process_f32(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0],
                                            C.byref(cl)), "d2pc_process_f32")
         self.last_cloud = cl
-        return cl.bytes_view().copy()
+        return cl.bytes_view().copy() if copy else cl.bytes_view()
 
     def submit(self, slot: int, frame):
         a = np.asarray(frame)
