@@ -80,6 +80,11 @@ def lib() -> C.CDLL:
         L.d2pc_oracle_fuse.restype = C.c_int
         L.d2pc_oracle_score_preprocess.argtypes = [_u8p, C.c_int, C.c_int, C.c_size_t, _i32p, C.c_int, _u8p]
         L.d2pc_oracle_score_preprocess.restype = C.c_int
+        L.d2pc_oracle_gaussian_blur_u8.argtypes = [_u8p, C.c_int, C.c_int, C.c_size_t, _i32p, C.c_int, C.c_double, C.c_int,
+                                                   _u8p, C.c_size_t]
+        L.d2pc_oracle_gaussian_blur_u8.restype = C.c_int
+        L.d2pc_oracle_sobel7_second_u8.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
+        L.d2pc_oracle_sobel7_second_u8.restype = None
         L.d2pc_oracle_colorize_depth.argtypes = [_u8p, C.c_int, C.c_int, C.c_size_t, _u8p]
         L.d2pc_oracle_colorize_depth.restype = None
         L.d2pc_oracle_run_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, _f64p,
@@ -241,6 +246,20 @@ def score_preprocess(frame: np.ndarray, rect, vertical: bool) -> np.ndarray:
     rc = lib().d2pc_oracle_score_preprocess(_p(frame, _u8p), w, h, w, _p(r, _i32p), 1 if vertical else 0, _p(out, _u8p))
     if rc != 0:
         raise ValueError("bad rectangle")
+    return out
+
+
+def gaussian_blur_u8(parent: np.ndarray, rect, ksize: int, sigma: float, submatrix: bool) -> np.ndarray:
+    """cv::GaussianBlur(parent(rect), dst, Size(ksize, ksize), sigma) on CV_8U; rect = (x, y, w, h).  submatrix is
+    Mat::isSubmatrix() of the source: True -> sepFilter2D with float32 kernels, False -> the fixed-point path."""
+    parent = np.ascontiguousarray(parent, dtype=np.uint8)
+    h, w = parent.shape
+    r = np.array(rect, dtype=np.int32)
+    out = np.empty((int(r[3]), int(r[2])), dtype=np.uint8)
+    rc = lib().d2pc_oracle_gaussian_blur_u8(_p(parent, _u8p), w, h, w, _p(r, _i32p), ksize, sigma, 1 if submatrix else 0,
+                                            _p(out, _u8p), out.strides[0])
+    if rc != 0:
+        raise ValueError(f"gaussian_blur_u8: {rc}")
     return out
 
 

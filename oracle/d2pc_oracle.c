@@ -524,6 +524,68 @@ static void gauss_fixed(const uint8_t *src, int sw, int sh, size_t step, const i
   free(rows);
 }
 
+/* cv::GaussianBlur on a CV_8U SUBMATRIX with the default (non-isolated) border does not take the fixed-point path:
+ * OpenCV 4.x guards it with `(borderType & BORDER_ISOLATED) || !src.isSubmatrix()` and otherwise falls through to
+ * sepFilter2D(src, dst, CV_8U, kx, ky) with the float32 kernels of getGaussianKernel.  That is the call the reference
+ * makes for its first blur (depth_map_fusion.cpp:70-71 / :89-90: cropped_score_k_ is mat(region), :264).  Pinned
+ * against cv2.sepFilter2D 4.13.0 (AVX2 dispatch): float32 row pass (taps in order 0..12), float32 symmetric column
+ * pass, then saturate_cast<uchar> (round half even); the vector loops use FMA, the scalar tails mul + add -- row
+ * pass: columns >= ow - ow % 32, column pass: columns >= ow - ow % 4 (ow = ROI width).  Border: reflect-101 at
+ * the edge of the PARENT image (the ROI sees the pixels around it).  getGaussianKernel(13, 3.0, CV_32F): */
+static const float kGauss13f[13] = {0x1.2fd344p-6f, 0x1.17e546p-5f, 0x1.cd7846p-5f, 0x1.54699ep-4f, 0x1.c16904p-4f,
+                                    0x1.09752ep-3f, 0x1.189f6cp-3f, 0x1.09752ep-3f, 0x1.c16904p-4f, 0x1.54699ep-4f,
+                                    0x1.cd7846p-5f, 0x1.17e546p-5f, 0x1.2fd344p-6f};
+
+static void gauss13_sepfilter(const uint8_t *src, int sw, int sh, size_t step, int x0, int y0, int ow, int oh,
+                              uint8_t *dst, size_t dst_step) {
+  const int r = 6, row_vec_end = ow - ow % 32, col_vec_end = ow - ow % 4;
+  const float *k = kGauss13f;
+  float *t = (float *)malloc(sizeof(float) * (size_t)(oh + 2 * r) * ow);
+  for (int yy = 0; yy < oh + 2 * r; ++yy) {
+    const uint8_t *s = src + (size_t)reflect101(y0 + yy - r, sh) * step;
+    for (int x = 0; x < ow; ++x) {
+      float acc = k[0] * (float)s[reflect101(x0 + x - r, sw)];
+      for (int i = 1; i < 13; ++i) {
+        const float v = (float)s[reflect101(x0 + x + i - r, sw)];
+        acc = x < row_vec_end ? fmaf(k[i], v, acc) : acc + k[i] * v;
+      }
+      t[(size_t)yy * ow + x] = acc;
+    }
+  }
+  for (int y = 0; y < oh; ++y)
+    for (int x = 0; x < ow; ++x) {
+      float acc = k[r] * t[(size_t)(y + r) * ow + x];
+      for (int j = 1; j <= r; ++j) {
+        const float v = t[(size_t)(y + r + j) * ow + x] + t[(size_t)(y + r - j) * ow + x];
+        acc = x < col_vec_end ? fmaf(k[r + j], v, acc) : acc + k[r + j] * v;
+      }
+      const float q = rintf(acc);
+      dst[(size_t)y * dst_step + x] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    }
+  free(t);
+}
+
+/* cv::GaussianBlur(roi, dst, Size(ksize, ksize), sigma) for the two calls the reference makes (13 / 3.0, 21 / 10.0),
+ * roi = rect of a parent image; `submatrix` is Mat::isSubmatrix() of the source (rect smaller than the parent). */
+int d2pc_oracle_gaussian_blur_u8(const uint8_t *parent, int pw, int ph, size_t step, const int rect[4], int ksize,
+                                 double sigma, int submatrix, uint8_t *dst, size_t dst_step) {
+  const int x0 = rect[0], y0 = rect[1], ow = rect[2], oh = rect[3];
+  if (ow <= 0 || oh <= 0 || x0 < 0 || y0 < 0 || x0 + ow > pw || y0 + oh > ph) return -1;
+  const int is13 = ksize == 13 && sigma == 3.0, is21 = ksize == 21 && sigma == 10.0;
+  if (!is13 && !is21) return -2;
+  if (submatrix) {
+    if (!is13) return -2;
+    gauss13_sepfilter(parent, pw, ph, step, x0, y0, ow, oh, dst, dst_step);
+    return 0;
+  }
+  /* not a submatrix: the fixed-point path; rect is the whole image */
+  uint8_t *tmp = (uint8_t *)malloc((size_t)ow * oh);
+  gauss_fixed(parent, pw, ph, step, is13 ? kGauss13 : kGauss21, ksize, x0, y0, ow, oh, tmp);
+  for (int y = 0; y < oh; ++y) memcpy(dst + (size_t)y * dst_step, tmp + (size_t)y * ow, (size_t)ow);
+  free(tmp);
+  return 0;
+}
+
 /* cv::Sobel(src, dst, -1, dx, dy, 7, 0.03) on an n x n CV_8U image, (dx,dy) = (0,2) or (2,0): separable float32
  * filter, kernels getDerivKernels(7): smoothing {1,6,15,20,15,6,1}, 2nd derivative {1,2,-1,-4,-1,2,1}; the
  * smoothing kernel is the one scaled (in float32).  The pass with the scaled kernel rounds at every step; OpenCV's
@@ -577,12 +639,19 @@ static void sobel7_second(const uint8_t *src, int n, int vertical, uint8_t *dst)
   free(t);
 }
 
+/* cv::Sobel(src, dst, -1, dx, dy, 7, 0.03) for (dx, dy) = (0, 2) [vertical = 0] or (2, 0) [vertical = 1] on a dense
+ * n x n CV_8U image (exported for the reference harness, oracle/ref_stubs). */
+void d2pc_oracle_sobel7_second_u8(const uint8_t *src, int n, int vertical, uint8_t *dst) {
+  sobel7_second(src, n, vertical, dst);
+}
+
 int d2pc_oracle_score_preprocess(const uint8_t *frame, int w, int h, size_t step, const int rect[4], int vertical,
                                  uint8_t *out) {
   const int x0 = rect[0], y0 = rect[1], n = rect[2];
   if (n <= 0 || rect[3] != n || x0 < 0 || y0 < 0 || x0 + n > w || y0 + n > h) return -1;
   uint8_t *g = (uint8_t *)malloc((size_t)n * n), *e = (uint8_t *)malloc((size_t)n * n);
-  gauss_fixed(frame, w, h, step, kGauss13, 13, x0, y0, n, n, g);            /* :70-71 / :89-90 */
+  /* :70-71 / :89-90: the source is the ROI mat(region) (:264), a submatrix unless the region is the whole frame */
+  d2pc_oracle_gaussian_blur_u8(frame, w, h, step, rect, 13, 3.0, n < w || n < h, g, (size_t)n);
   sobel7_second(g, n, vertical, e);                                            /* :72 / :91 */
   for (size_t i = 0; i < (size_t)n * n; ++i) e[i] = e[i] > 30 ? 255 : 0;       /* :73 / :92 THRESH_BINARY */
   gauss_fixed(e, n, n, (size_t)n, kGauss21, 21, 0, 0, n, n, g);              /* :74-75 / :93-94 */

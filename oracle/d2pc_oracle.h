@@ -135,12 +135,25 @@ int d2pc_oracle_fuse(const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
 /* src/depth_map_fusion.cpp:64-80 (vertical = 0, MatchingScoreCb1) / :82-99 (vertical = 1, MatchingScoreCb2):
  * what the node caches as cropped_score_k_ (== cropped_score_k_grad_) for a score frame (already rotated for
  * callback 2) and its cropToSquare rectangle rect = {x, y, n, n}:
- *   GaussianBlur 13x13 sigma 3 (the crop is a non-isolated ROI: the blur sees the frame around it) ->
- *   Sobel 2nd derivative ksize 7 scale 0.03 -> threshold 30 -> GaussianBlur 21x21 sigma 10 -> score + 2*grad.
- * Arithmetic pinned against cv2 4.13.0 (AVX2 dispatch): 8.8 fixed-point Gaussian kernels, float32 Sobel whose
- * scaled pass uses FMA except in the SIMD tail columns.  out is n x n dense.  Returns 0, -1 on bad geometry. */
+ *   GaussianBlur 13x13 sigma 3 (the crop is a non-isolated submatrix: the blur sees the frame around it and, being
+ *   a submatrix, runs as sepFilter2D with float32 kernels, not OpenCV's fixed-point path) ->
+ *   Sobel 2nd derivative ksize 7 scale 0.03 -> threshold 30 -> GaussianBlur 21x21 sigma 10 (stand-alone Mat: the
+ *   fixed-point path) -> score + 2*grad.
+ * Arithmetic pinned against cv2 4.13.0 (AVX2 dispatch): float32 separable filters whose vector loops use FMA and
+ * whose scalar tail columns do not; 8.8 fixed-point kernel for the second blur.  out is n x n dense.
+ * Returns 0, -1 on bad geometry. */
 int d2pc_oracle_score_preprocess(const uint8_t *frame, int w, int h, size_t step, const int rect[4], int vertical,
                                  uint8_t *out);
+
+/* cv::GaussianBlur(parent(rect), dst, Size(ksize, ksize), sigma) on CV_8U for the two calls the reference makes
+ * (13 / 3.0 at depth_map_fusion.cpp:70-71, :89-90 and 21 / 10.0 at :74-75, :93-94).  submatrix = Mat::isSubmatrix()
+ * of the source: OpenCV 4.x runs its fixed-point path only for non-submatrix (or isolated-border) sources and
+ * sepFilter2D with float32 kernels otherwise.  Returns 0, -1 bad rectangle, -2 unsupported kernel. */
+int d2pc_oracle_gaussian_blur_u8(const uint8_t *parent, int pw, int ph, size_t step, const int rect[4], int ksize,
+                                 double sigma, int submatrix, uint8_t *dst, size_t dst_step);
+
+/* cv::Sobel(src, dst, -1, dx, dy, 7, 0.03), (dx, dy) = (0, 2) [vertical = 0] / (2, 0) [vertical = 1], n x n dense. */
+void d2pc_oracle_sobel7_second_u8(const uint8_t *src, int n, int vertical, uint8_t *dst);
 
 /* src/depth_map_fusion.cpp:304-358 colorizeDepth (the RAINBOW_WITH_BLACK debug views); rgb is w*h*3 dense. */
 void d2pc_oracle_colorize_depth(const uint8_t *gray, int w, int h, size_t step, uint8_t *rgb);

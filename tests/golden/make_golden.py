@@ -125,11 +125,80 @@ def score_preprocess_cv(score, vertical):
     return cv2.add(score, cv2.add(g, g))  # score + 2*grad, saturating u8 MatExpr
 
 
+def _f32(a):
+    return np.asarray(a, dtype=np.float32)
+
+
+def _fma32(k, v, acc):
+    """float32 fused multiply-add, elementwise: k scalar, v / acc float32 arrays.  k * v is exact in float64 (24 x 24
+    bits), so the only way float64 arithmetic can differ from a true FMA is double rounding: the float64 sum landing
+    exactly on a float32 rounding boundary.  That case is refused rather than guessed."""
+    a, b = np.float64(k) * v.astype(np.float64), acc.astype(np.float64)
+    t = a + b
+    bb = t - a
+    err = (a - (t - bb)) + (b - bb)  # exact error of the float64 addition (two-sum)
+    low = t.view(np.uint64) & np.uint64((1 << 29) - 1)
+    assert not np.any((err != 0) & (low == np.uint64(1 << 28))), "double-rounding hazard: regenerate with another seed"
+    return t.astype(np.float32)
+
+
+def gauss13_submatrix(frame, x, y, w, h):
+    """cv::GaussianBlur(frame(Rect(x, y, w, h)), dst, Size(13, 13), 3.0) for a CV_8U SUBMATRIX source, default
+    border -- the reference's first blur (src/depth_map_fusion.cpp:70-71 / :89-90).  OpenCV 4.x enters its
+    fixed-point Gaussian only if `(borderType & BORDER_ISOLATED) || !src.isSubmatrix()`; a submatrix falls through
+    to sepFilter2D(src, dst, CV_8U, kx, ky) with kx = ky = getGaussianKernel(13, 3, CV_32F).  Python cannot hand
+    cv2 a Mat with the SUBMATRIX flag (a numpy view arrives as a stand-alone Mat with a step), so that call is
+    restated here in numpy and pinned against cv2.sepFilter2D where cv2 can express it (check_sepfilter_model):
+      * float32 row pass, taps in order 0..12; float32 symmetric column pass; saturate_cast<uchar> (rint);
+      * the AVX2 vector loops fuse multiply-add, the scalar tails do not: row pass columns >= w - w % 32, column
+        pass columns >= w - w % 4, w being the width of the filtered Mat, i.e. of the ROI;
+      * non-isolated border: the pixels around the ROI, reflect-101 only at the edge of the whole frame."""
+    k = cv2.getGaussianKernel(13, 3.0, cv2.CV_32F).ravel()
+    pad = cv2.copyMakeBorder(frame, 6, 6, 6, 6, cv2.BORDER_REFLECT_101)
+    p = pad[y:y + h + 12, x:x + w + 12].astype(np.float32)
+    rv, cv_ = w - w % 32, w - w % 4
+    acc_f = _f32(k[0] * p[:, 0:w])
+    acc_m = acc_f.copy()
+    for i in range(1, 13):
+        t = p[:, i:i + w]
+        acc_f = _fma32(k[i], t, acc_f)
+        acc_m = _f32(acc_m + _f32(k[i] * t))
+    rows = acc_f
+    rows[:, rv:] = acc_m[:, rv:]
+    acc_f = _f32(k[6] * rows[6:6 + h])
+    acc_m = acc_f.copy()
+    for j in range(1, 7):
+        t = _f32(rows[6 + j:6 + j + h] + rows[6 - j:6 - j + h])
+        acc_f = _fma32(k[6 + j], t, acc_f)
+        acc_m = _f32(acc_m + _f32(k[6 + j] * t))
+    cols = acc_f
+    cols[:, cv_:] = acc_m[:, cv_:]
+    return np.clip(np.rint(cols), 0, 255).astype(np.uint8)
+
+
+def check_sepfilter_model(rng):
+    """gauss13_submatrix against cv2.sepFilter2D in the two situations cv2 can be driven into from Python:
+    (a) the ROI is a whole stand-alone image (every tail rule, border = the image's own edge);
+    (b) a ROI inside a frame, compared with sepFilter2D of the whole frame on the columns whose vector / tail
+        status is the same in both calls (the border pixels then come from around the ROI)."""
+    k = cv2.getGaussianKernel(13, 3.0, cv2.CV_32F)
+    for (h, w) in [(64, 95), (50, 63), (90, 130), (40, 31), (33, 705), (20, 4), (20, 3)]:
+        img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+        assert np.array_equal(gauss13_submatrix(img, 0, 0, w, h), cv2.sepFilter2D(img, cv2.CV_8U, k, k)), (h, w)
+    frame = rng.integers(0, 256, size=(96, 160), dtype=np.uint8)   # 160 % 32 == 0: the frame call has no tails
+    full = cv2.sepFilter2D(frame, cv2.CV_8U, k, k)
+    for (x, y, w, h) in [(0, 0, 64, 64), (32, 5, 96, 80), (96, 16, 64, 64), (3, 2, 128, 90)]:
+        assert np.array_equal(gauss13_submatrix(frame, x, y, w, h), full[y:y + h, x:x + w]), (x, y, w, h)
+
+
 def score_chain(frame, x, y, n, vertical):
     """MatchingScoreCb1 (vertical=False, src/depth_map_fusion.cpp:64-80) / Cb2 (True, :82-99) for a score frame
     (already rotated for Cb2) and its cropToSquare rectangle."""
     score = frame[y:y + n, x:x + n].copy()
-    g = cv2.GaussianBlur(frame, (13, 13), 3.0)[y:y + n, x:x + n].copy()
+    if n < frame.shape[0] or n < frame.shape[1]:      # mat(region) is a submatrix: sepFilter2D path
+        g = gauss13_submatrix(frame, x, y, n, n)
+    else:                                             # the region is the whole frame: fixed-point path
+        g = cv2.GaussianBlur(frame, (13, 13), 3.0)
     if vertical:
         g = cv2.Sobel(g, -1, 2, 0, ksize=7, scale=0.03)
     else:
@@ -219,9 +288,10 @@ def main():
         sp[f"sob_v{i}"] = cv2.Sobel(sp[f"g13_{i}"], -1, 2, 0, ksize=7, scale=0.03)
     np.savez_compressed(os.path.join(HERE, "score_golden.npz"), **sp)
     # ---- the whole MatchingScoreCb chain on full frames, ROI semantics included ------------------------------
-    # cropped_score_k_ is a non-isolated ROI of the (rotated) frame, so the first GaussianBlur sees the pixels
-    # around the ROI: equivalent to blurring the whole frame and cropping.  Everything after that runs on a
-    # stand-alone n x n Mat (reflect-101 at its own edge).
+    # cropped_score_k_ is a non-isolated ROI (a submatrix) of the (rotated) frame: the first GaussianBlur sees the
+    # pixels around the ROI and runs as sepFilter2D, not as the fixed-point Gaussian (gauss13_submatrix).
+    # Everything after that runs on a stand-alone n x n Mat (reflect-101 at its own edge).
+    check_sepfilter_model(np.random.default_rng(77))
     ch = {}
     for i, (h, w, ox, oy) in enumerate([(150, 200, -7, 15), (160, 120, 5, -9), (300, 424, -7, 15)]):
         s1 = cv2.GaussianBlur(rng.integers(0, 256, size=(h, w), dtype=np.uint8), (7, 7), 2.0)
@@ -240,6 +310,22 @@ def main():
         else:
             ch.update({f"s1_{i}": s1, f"s2_{i}": s2, f"off_{i}": np.array([ox, oy]), f"pre1_{i}": pre1, f"pre2_{i}": pre2})
     np.savez_compressed(os.path.join(HERE, "score_chain_golden.npz"), **ch)
+    # ---- the sepFilter2D Gaussian on its own: stand-alone images straight from cv2 (tail rules at several widths)
+    # and ROIs of a frame (non-isolated border) from the numpy restatement that check_sepfilter_model pins ---------
+    sf = {}
+    k13 = cv2.getGaussianKernel(13, 3.0, cv2.CV_32F)
+    sf["kernel13"] = k13.ravel()
+    for i, (h, w) in enumerate([(40, 95), (33, 130), (50, 31), (24, 64)]):
+        img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+        sf[f"img{i}"] = img
+        sf[f"sep{i}"] = cv2.sepFilter2D(img, cv2.CV_8U, k13, k13)
+    frame = rng.integers(0, 256, size=(90, 150), dtype=np.uint8)
+    sf["frame"] = frame
+    rects = np.array([[0, 0, 70, 70], [10, 5, 101, 77], [80, 20, 70, 70], [3, 2, 140, 86]])
+    sf["rects"] = rects
+    for i, (x, y, w, h) in enumerate(rects):
+        sf[f"roi{i}"] = gauss13_submatrix(frame, int(x), int(y), int(w), int(h))
+    np.savez_compressed(os.path.join(HERE, "sepfilter_golden.npz"), **sf)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -159,6 +159,26 @@ def test_score_preprocess_chain_cv2():
         assert_same_bits(oracle.score_preprocess(oracle.rotate_cw(s2), r2, True), g[f"pre2_{i}"], f"MatchingScoreCb2 #{i}")
 
 
+def test_sepfilter_gaussian_cv2():
+    """The first blur of MatchingScoreCb1/2 runs on a submatrix, i.e. as sepFilter2D with float32 kernels
+    (oracle/d2pc_oracle.c gauss13_sepfilter): stand-alone images straight from cv2.sepFilter2D (vector / tail
+    columns at four widths), ROIs of a frame from the generator's cv2-pinned restatement."""
+    g = golden("sepfilter_golden.npz")
+    for i in range(4):
+        img = g[f"img{i}"]
+        h, w = img.shape
+        assert_same_bits(oracle.gaussian_blur_u8(img, (0, 0, w, h), 13, 3.0, True), g[f"sep{i}"], f"stand-alone #{i}")
+    for i, r in enumerate(g["rects"]):
+        assert_same_bits(oracle.gaussian_blur_u8(g["frame"], tuple(int(v) for v in r), 13, 3.0, True), g[f"roi{i}"],
+                         f"ROI #{i}")
+    # and the fixed-point path is what a non-submatrix source still gets (score_golden.npz g13_* are cv2.GaussianBlur)
+    sg = golden("score_golden.npz")
+    for i in range(2):
+        base = sg[f"score{i}"]
+        h, w = base.shape
+        assert_same_bits(oracle.gaussian_blur_u8(base, (0, 0, w, h), 13, 3.0, False), sg[f"g13_{i}"], f"fixed point #{i}")
+
+
 def test_colorize_depth_known_answers():
     # src/depth_map_fusion.cpp:304-358, bytes in the order the reference stores them
     ramp = np.arange(256, dtype=np.uint8).reshape(1, 256)

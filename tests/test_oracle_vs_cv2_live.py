@@ -36,3 +36,24 @@ def test_q_random_intrinsics():
         out = cv2.stereoRectify(K, np.zeros((5, 1)), K, np.zeros((5, 1)), (752, 480), np.eye(3),
                                 np.array([[-b], [0.0], [0.0]]))
         assert oracle.q_from_intrinsics(fx, fy, cx, cy, b).tobytes() == out[4].tobytes()
+
+
+@pytest.mark.parametrize("n", [705, 450, 465, 96])
+def test_sepfilter_gaussian_live_at_the_reference_sizes(n):
+    """cv::GaussianBlur on a submatrix = sepFilter2D with float32 kernels (what the reference's first blur runs as,
+    src/depth_map_fusion.cpp:70-71): the oracle against cv2.sepFilter2D at the crop sizes of the BASELINE frames
+    (705 at 1280x720, 465 at 752x480 / 640x480 with the launch offsets).  A different cv2 build (other SIMD width,
+    no FMA) fails here loudly rather than silently."""
+    rng = np.random.default_rng(n)
+    k = cv2.getGaussianKernel(13, 3.0, cv2.CV_32F)
+    for _ in range(3):
+        img = rng.integers(0, 256, size=(n, n), dtype=np.uint8)
+        want = cv2.sepFilter2D(img, cv2.CV_8U, k, k)
+        assert np.array_equal(oracle.gaussian_blur_u8(img, (0, 0, n, n), 13, 3.0, True), want)
+    # non-isolated border: a ROI whose tails coincide with the frame's (frame width % 32 == 0, ROI flush right)
+    frame = rng.integers(0, 256, size=(n + 20, 32 * ((n + 64) // 32)), dtype=np.uint8)
+    full = cv2.sepFilter2D(frame, cv2.CV_8U, k, k)
+    w = 32 * (n // 32)
+    x = frame.shape[1] - w
+    got = oracle.gaussian_blur_u8(frame, (x, 7, w, n), 13, 3.0, True)
+    assert np.array_equal(got, full[7:7 + n, x:x + w])
