@@ -73,7 +73,7 @@ struct d2pc_ctx {
   // fusion buffers
   DevBuf d_fuse_in[4], d_container, d_combined, d_fused;
   PinBuf h_fused, h_combined;
-  DevBuf d_score_in, d_score_scratch, d_score_out[2];
+  DevBuf d_score_in, d_score_out[2];
   PinBuf h_score[2];
   DevBuf d_color_in, d_color_out, d_color_lut;
   PinBuf h_color;
@@ -516,7 +516,7 @@ void d2pc_destroy(d2pc_ctx *ctx) {
   for (auto &b : ctx->d_fuse_in) free_dev(b);
   free_dev(ctx->d_container), free_dev(ctx->d_combined), free_dev(ctx->d_fused);
   free_pin(ctx->h_fused), free_pin(ctx->h_combined);
-  free_dev(ctx->d_score_in), free_dev(ctx->d_score_scratch), free_dev(ctx->d_score_out[0]), free_dev(ctx->d_score_out[1]);
+  free_dev(ctx->d_score_in), free_dev(ctx->d_score_out[0]), free_dev(ctx->d_score_out[1]);
   free_pin(ctx->h_score[0]), free_pin(ctx->h_score[1]);
   free_dev(ctx->d_color_in), free_dev(ctx->d_color_out), free_dev(ctx->d_color_lut), free_pin(ctx->h_color);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
@@ -877,17 +877,15 @@ static int score_device_impl(d2pc_ctx *ctx, const uint8_t *d_score, uint32_t w, 
                              uint8_t *d_out, int *n_out) {
   const d2pc_config &c = ctx->cfg;
   FuseGeometry g;
-  if (!fuse_geometry((int)w, (int)h, c.offset_x, c.offset_y, c.fuse_crop_left, c.fuse_crop_right, c.fuse_crop_top,
-                     c.fuse_crop_bottom, &g))
+  fuse_geometry((int)w, (int)h, c.offset_x, c.offset_y, c.fuse_crop_left, c.fuse_crop_right, c.fuse_crop_top,
+                c.fuse_crop_bottom, &g);
+  // MatchingScoreCb only needs its own cropToSquare rectangle to lie inside the (rotated) frame (:66 / :85); the
+  // rest of the fusion geometry (container, final trim) is publishFusedDepthMap's business.
+  const int *rr = which == 2 ? g.r2 : g.r1;
+  const int fc = which == 2 ? (int)h : (int)w, fr = which == 2 ? (int)w : (int)h;
+  if (rr[2] <= 0 || rr[3] != rr[2] || rr[0] < 0 || rr[1] < 0 || rr[0] + rr[2] > fc || rr[1] + rr[3] > fr)
     return D2PC_ERR_GEOMETRY;
-  const int n = g.n;
-  int rc;
-  const size_t need = score_scratch_bytes(n);
-  if (need > ctx->d_score_scratch.cap) {
-    CU(ctx, cudaStreamSynchronize(ctx->s_compute));
-    if ((rc = grow_dev(ctx, ctx->d_score_scratch, need))) return rc;
-  }
-  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  const int n = rr[2];
   ScoreLaunch L;
   L.frame = d_score;
   L.step = step;
@@ -895,14 +893,6 @@ static int score_device_impl(d2pc_ctx *ctx, const uint8_t *d_score, uint32_t w, 
   L.rotated = which == 2;
   const int *r = which == 2 ? g.r2 : g.r1;  // :66 cropToSquare(image, ox, oy) / :85 cropToSquare(rot, -ox, -oy)
   for (int i = 0; i < 4; ++i) L.rect[i] = r[i];
-  uint8_t *p = ctx->d_score_scratch.p;
-  L.rows16 = reinterpret_cast<uint16_t *>(p);
-  p += al((size_t)(n + 20) * n * 2);
-  L.f32 = reinterpret_cast<float *>(p);
-  p += al((size_t)n * n * 4);
-  L.tmp8a = p;
-  p += al((size_t)n * n);
-  L.tmp8b = p;
   L.out = d_out;
   int nl = 0;
   CU(ctx, launch_score_preprocess(L, ctx->s_compute, &nl));

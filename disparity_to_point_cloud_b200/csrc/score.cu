@@ -1,4 +1,4 @@
-// score.cu -- depth_map_fusion's matching-score preprocessing on sm_100a.
+// score.cu -- depth_map_fusion's matching-score preprocessing on sm_100a, one fused tile kernel per callback.
 //
 // Replaces, for MatchingScoreCb1 (src/depth_map_fusion.cpp:64-80) and MatchingScoreCb2 (:82-99):
 //   cv::GaussianBlur(score, grad, Size(13,13), 3.0)          :70-71 / :89-90
@@ -8,20 +8,46 @@
 //   grad = score + 2 * grad  (saturating)                    :76    / :95
 // and the rotateMat + cropToSquare in front of callback 2 (:84-85) as index arithmetic.
 //
-// The arithmetic is OpenCV's, pinned against cv2 4.13.0 (tests/golden/score_chain_golden.npz):
-//   * GaussianBlur on CV_8U is fixed point: kernel quantised to 8 fractional bits (error-diffused so it sums to
-//     256), rows -> 8.8, columns -> 16.16, round half up.  Border reflect-101.  The first blur runs on a
-//     non-isolated ROI, i.e. it sees the frame around the crop and reflects only at the frame edge.
-//   * Sobel ksize 7 is a separable float32 filter; the smoothing kernel carries the 0.03 scale (in float32).  The
-//     pass with the scaled kernel rounds at every step and OpenCV's AVX2 code uses FMA in its vector loop but
-//     mul+add in the scalar tail (row pass: 32-column vectors; symmetric column pass: 4-column vectors).
-// These images are small (n = 705 at 1280x720); the kernels are one thread per output pixel, cache-served.
+// The arithmetic is OpenCV's, pinned against cv2 4.13.0 (tests/golden/score_chain_golden.npz, sepfilter_golden.npz):
+//   * The FIRST blur runs on cropped_score_k_ = mat(region) (:264), a SUBMATRIX with the default non-isolated
+//     border.  OpenCV 4.x keeps such a source out of its fixed-point Gaussian and runs sepFilter2D with the float32
+//     kernel of getGaussianKernel(13, 3): float32 row pass (taps 0..12 in order), float32 symmetric column pass,
+//     round half even.  Its AVX2 vector loops fuse multiply-add, the scalar tails do not (row pass: columns
+//     >= n - n % 32, column pass: columns >= n - n % 4).  The border is the frame around the crop, reflect-101 only
+//     at the frame's own edge.  (When the crop is the whole frame it is not a submatrix and takes the fixed-point
+//     path like the second blur.)
+//   * Sobel ksize 7 is the same float32 separable engine; the smoothing kernel carries the 0.03 scale.
+//   * The SECOND blur runs on a stand-alone Mat: OpenCV's fixed-point Gaussian (kernel quantised to 8 fractional
+//     bits summing to 256, rows 8.8, columns 16.16, round half up), reflect-101 at the n x n edge.
+//
+// One CTA produces a 64 x 64 output tile from the 102 x 102 frame pixels under it (halo 6 + 3 + 10), every
+// intermediate in shared memory (55 KB): four global intermediates and six launches of the first version are gone.
+// An intermediate array is indexed by EXTENDED crop coordinates and holds stage(reflect101(coordinate)), so the
+// reflect-101 border of the stand-alone stages is a plain array read.
 #include "score.h"
 
 namespace d2pc {
 namespace {
 
-__constant__ int c_gauss13[13] = {5, 8, 15, 21, 28, 33, 36, 33, 28, 21, 15, 8, 5};
+constexpr int kT = 64;              // output tile
+constexpr int kHE = 10;             // halo of the thresholded edge image (second blur, 21 taps)
+constexpr int kHG = kHE + 3;        // + Sobel 7
+constexpr int kHF = kHG + 6;        // + first blur 13
+constexpr int kEW = kT + 2 * kHE;   // 84
+constexpr int kGW = kT + 2 * kHG;   // 90
+constexpr int kFW = kT + 2 * kHF;   // 102
+constexpr int kFP = 104, kGP = 92;  // byte pitches of the u8 arrays F and G (E reuses F's storage with pitch kEW)
+constexpr int kThreads = 1024;
+constexpr size_t kSmemF = (size_t)kFW * kFP;                // 10,608: frame tile, later the edge image E (84 x 84)
+constexpr size_t kSmemR = (size_t)kFW * kGW * sizeof(float);  // 36,720: row-pass results (float / u16)
+constexpr size_t kSmemG = (size_t)kGW * kGP;                // 8,280: first blur, u8
+constexpr size_t kSmemS = (size_t)kT * kT;                  // 4,096: the score pixels of the tile
+constexpr size_t kSmemTotal = kSmemF + kSmemR + kSmemG + kSmemS;
+
+__constant__ float c_gauss13f[13] = {0x1.2fd344p-6f, 0x1.17e546p-5f, 0x1.cd7846p-5f, 0x1.54699ep-4f, 0x1.c16904p-4f,
+                                     0x1.09752ep-3f, 0x1.189f6cp-3f, 0x1.09752ep-3f, 0x1.c16904p-4f, 0x1.54699ep-4f,
+                                     0x1.cd7846p-5f, 0x1.17e546p-5f, 0x1.2fd344p-6f};  // getGaussianKernel(13, 3, CV_32F)
+__constant__ int c_gauss13[13] = {5, 8, 15, 21, 28, 33, 36, 33, 28, 21, 15, 8, 5};  // fixed-point path
 __constant__ int c_gauss21[21] = {9, 9, 11, 11, 12, 13, 13, 14, 14, 15, 14, 15, 14, 14, 13, 13, 12, 11, 11, 9, 9};
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -30,160 +56,221 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
-struct Src {  // a mono8 image, optionally viewed through rotateMat (rot(r, c) = src(h-1-c, r))
-  const uint8_t *p;
+// A reflected coordinate that some output of the tile really needs always lies within `halo` of the tile; array
+// positions far past the image edge (a partial last tile) reflect further away, feed nothing, and are clamped so
+// that their reads stay inside the arrays.
+__device__ __forceinline__ int in_tile(int r, int t0, int halo) { return min(max(r, t0 - halo), t0 + kT - 1 + halo); }
+
+struct ScoreArgs {
+  const uint8_t *frame;  // stored frame (w x h, `step` bytes per row)
   size_t step;
-  int w, h;  // of the stored image
-  bool rotated;
-  __device__ __forceinline__ int cols() const { return rotated ? h : w; }
-  __device__ __forceinline__ int rows() const { return rotated ? w : h; }
-  __device__ __forceinline__ int at(int x, int y) const {
-    return rotated ? p[(size_t)(h - 1 - x) * step + y] : p[(size_t)y * step + x];
-  }
+  int w, h;
+  int rotated;     // the chain runs on rotateMat(frame): rot(r, c) = frame(h - 1 - c, r); h cols x w rows
+  int rx, ry, n;   // cropToSquare rectangle in the (rotated) frame
+  int submatrix;   // the rectangle is smaller than the (rotated) frame: first blur = sepFilter2D (float32)
+  float ks[7];     // Sobel smoothing kernel {1,6,15,20,15,6,1} * 0.03f, computed in float32 on the host
+  uint8_t *out;    // n x n dense
 };
 
-// Score 2 is read through rotateMat: walking along a row of the rotated image walks down a column of the stored
-// frame, so a row filter over it would make 13 uncoalesced reads per output.  The (n + 12)^2 neighbourhood of the
-// crop (reflect-101 at the frame edge, as the non-isolated ROI sees it) is therefore materialised once, through a
-// 32 x 32 shared-memory tile: reads run along the stored rows, writes along the rows of the rotated view.
-__global__ void __launch_bounds__(256) rotcrop_kernel(Src s, int x0, int y0, int m, uint8_t *out) {
-  __shared__ uint8_t tile[32][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int xx = blockIdx.x * 32 + ty + 8 * j, yy = blockIdx.y * 32 + tx;
-    if (xx < m && yy < m) tile[ty + 8 * j][tx] = (uint8_t)s.at(reflect101(x0 + xx, s.cols()), reflect101(y0 + yy, s.rows()));
+__global__ void __launch_bounds__(kThreads) score_tile_kernel(const __grid_constant__ ScoreArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t *F = smem;                                        // [kFW][kFP]
+  float *R = reinterpret_cast<float *>(smem + kSmemF);      // row-pass scratch
+  uint8_t *G = smem + kSmemF + kSmemR;                      // [kGW][kGP]
+  uint8_t *S = G + kSmemG;                                  // [kT][kT]
+  uint8_t *E = F;                                           // [kEW][kEW], after F is dead
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const int n = a.n;
+  const int tx0 = blockIdx.x * kT, ty0 = blockIdx.y * kT;   // crop coordinates of the tile
+  const int cols = a.rotated ? a.h : a.w, rows = a.rotated ? a.w : a.h;  // of the (rotated) frame
+  // every stage below: a warp takes a row of the stage's array, its lanes the columns (no index divisions)
+
+  // ---- F: the frame under the tile, extended crop coordinates [t0 - 19, t0 + 83); non-isolated border =
+  // the pixels around the crop, reflect-101 at the frame edge.  For the rotated view a warp takes a COLUMN of F:
+  // its lanes walk down the rotated rows, i.e. along a stored row (coalesced), and the tile is written transposed.
+  for (int u = warp; u < kFW; u += kWarps) {
+    if (!a.rotated) {
+      const uint8_t *row = a.frame + (size_t)reflect101(a.ry + ty0 - kHF + u, rows) * a.step;
+      for (int v = lane; v < kFW; v += 32) F[u * kFP + v] = row[reflect101(a.rx + tx0 - kHF + v, cols)];
+    } else {
+      const uint8_t *row = a.frame + (size_t)(a.h - 1 - reflect101(a.rx + tx0 - kHF + u, cols)) * a.step;
+      for (int v = lane; v < kFW; v += 32) F[v * kFP + u] = row[reflect101(a.ry + ty0 - kHF + v, rows)];
+    }
   }
   __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int xx = blockIdx.x * 32 + tx, yy = blockIdx.y * 32 + ty + 8 * j;
-    if (xx < m && yy < m) out[(size_t)yy * m + xx] = tile[tx][ty + 8 * j];
-  }
-}
+  // the score pixels of the tile itself (for the last step; F is overwritten before that)
+  for (int y = warp; y < kT; y += kWarps)
+    for (int x = lane; x < kT; x += 32) S[y * kT + x] = F[(y + kHF) * kFP + x + kHF];
 
-// rows pass of the fixed-point Gaussian: out16[(yy) * ow + x], yy in [0, oh + 2r), source row y0 + yy - r
-template <int KS>
-__global__ void gauss_rows_kernel(Src s, int x0, int y0, int ow, int oh, uint16_t *out16) {
-  constexpr int R = KS / 2;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y;
-  if (x >= ow) return;
-  const int *k = KS == 13 ? c_gauss13 : c_gauss21;
-  const int sy = reflect101(y0 + yy - R, s.rows());
-  uint32_t acc = 0;
+  // ---- first blur -> G(gy, gx) for extended coordinates [t0 - 13, t0 + 77)
+  if (a.submatrix) {
+    // rows: R(fy, gc) over all F rows and the G columns; taps in order, FMA in the vector columns
+    const int row_vec_end = n - n % 32, col_vec_end = n - n % 4;
+    for (int fy = warp; fy < kFW; fy += kWarps)
+      for (int gc = lane; gc < kGW; gc += 32) {
+        const int c = tx0 - kHG + gc;          // crop column (the tail rule only matters for 0 <= c < n)
+        const uint8_t *p = F + fy * kFP + gc;  // F column of crop column c - 6
+        const bool fma = c < row_vec_end;
+        float s = __fmul_rn(c_gauss13f[0], (float)p[0]);
 #pragma unroll
-  for (int i = 0; i < KS; ++i) acc += (uint32_t)k[i] * (uint32_t)s.at(reflect101(x0 + x + i - R, s.cols()), sy);
-  out16[(size_t)yy * ow + x] = (uint16_t)acc;  // 8.8, <= 255 * 256
-}
-
-// columns pass; kAddScore: out = sat(score + 2 * g) with score read from the (rotated) frame rectangle
-template <int KS, bool kAddScore>
-__global__ void gauss_cols_kernel(const uint16_t *rows16, int ow, int oh, Src score, int x0, int y0, uint8_t *out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= ow) return;
-  const int *k = KS == 13 ? c_gauss13 : c_gauss21;
-  uint32_t acc = 0;
+        for (int k = 1; k < 13; ++k) {
+          const float v = (float)p[k];
+          s = fma ? __fmaf_rn(c_gauss13f[k], v, s) : __fadd_rn(s, __fmul_rn(c_gauss13f[k], v));
+        }
+        R[fy * kGW + gc] = s;
+      }
+    __syncthreads();
+    for (int gy = warp; gy < kGW; gy += kWarps) {
+      const int ry = in_tile(reflect101(ty0 - kHG + gy, n), ty0, kHG);
+      for (int gx = lane; gx < kGW; gx += 32) {
+        const int rx = in_tile(reflect101(tx0 - kHG + gx, n), tx0, kHG);
+        const float *t = R + (ry - (ty0 - kHF)) * kGW + (rx - (tx0 - kHG));  // R row of crop row ry, column rx
+        const bool fma = rx < col_vec_end;
+        float s = __fmul_rn(c_gauss13f[6], t[0]);
 #pragma unroll
-  for (int i = 0; i < KS; ++i) acc += (uint32_t)k[i] * (uint32_t)rows16[(size_t)(y + i) * ow + x];
-  uint32_t v = min((acc + 32768u) >> 16, 255u);
-  if constexpr (kAddScore) v = min((uint32_t)score.at(x0 + x, y0 + y) + 2u * v, 255u);
-  out[(size_t)y * ow + x] = (uint8_t)v;
-}
-
-struct SobelK {
-  float ks[7];  // smoothing kernel {1,6,15,20,15,6,1} * 0.03f, computed in float32 on the host
-};
-
-// Sobel rows pass.  vertical == false (dx = 0, dy = 2): scaled smoothing kernel, sequential k = 0..6, FMA for
-// columns < n - n % 32.  vertical == true (dx = 2, dy = 0): integer 2nd-derivative kernel (exact).
-__global__ void sobel_rows_kernel(const uint8_t *src, int n, bool vertical, SobelK K, float *t) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= n) return;
-  const uint8_t *row = src + (size_t)y * n;
-  float s;
-  if (!vertical) {
-    const bool fma = x < n - n % 32;
-    s = __fmul_rn(K.ks[0], (float)row[reflect101(x - 3, n)]);
-#pragma unroll
-    for (int i = 1; i < 7; ++i) {
-      const float v = (float)row[reflect101(x + i - 3, n)];
-      s = fma ? __fmaf_rn(K.ks[i], v, s) : __fadd_rn(s, __fmul_rn(K.ks[i], v));
+        for (int j = 1; j <= 6; ++j) {
+          const float v = __fadd_rn(t[j * kGW], t[-j * kGW]);
+          s = fma ? __fmaf_rn(c_gauss13f[6 + j], v, s) : __fadd_rn(s, __fmul_rn(c_gauss13f[6 + j], v));
+        }
+        G[gy * kGP + gx] = (uint8_t)fminf(fmaxf(rintf(s), 0.f), 255.f);
+      }
     }
   } else {
-    const float d[7] = {1.f, 2.f, -1.f, -4.f, -1.f, 2.f, 1.f};
-    s = 0.f;
+    // the crop is the whole frame: fixed-point Gaussian (8.8 rows, 16.16 columns, round half up)
+    uint32_t *R32 = reinterpret_cast<uint32_t *>(R);
+    for (int fy = warp; fy < kFW; fy += kWarps)
+      for (int gc = lane; gc < kGW; gc += 32) {
+        const uint8_t *p = F + fy * kFP + gc;
+        uint32_t acc = 0;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) s = __fadd_rn(s, __fmul_rn(d[i], (float)row[reflect101(x + i - 3, n)]));
-  }
-  t[(size_t)y * n + x] = s;
-}
-
-// Sobel columns pass (symmetric form) + saturate_cast<uchar> (round half even) + threshold(30, 255, BINARY).
-__global__ void sobel_cols_thresh_kernel(const float *t, int n, bool vertical, SobelK K, uint8_t *out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= n) return;
-  float s;
-  if (!vertical) {
-    const float d[4] = {-4.f, -1.f, 2.f, 1.f};  // centre, +-1, +-2, +-3 of {1,2,-1,-4,-1,2,1}; exact in float32
-    s = __fmul_rn(d[0], t[(size_t)y * n + x]);
+        for (int k = 0; k < 13; ++k) acc += (uint32_t)c_gauss13[k] * p[k];
+        R32[fy * kGW + gc] = acc;
+      }
+    __syncthreads();
+    for (int gy = warp; gy < kGW; gy += kWarps) {
+      const int ry = in_tile(reflect101(ty0 - kHG + gy, n), ty0, kHG);
+      for (int gx = lane; gx < kGW; gx += 32) {
+        const int rx = in_tile(reflect101(tx0 - kHG + gx, n), tx0, kHG);
+        const uint32_t *t = R32 + (ry - (ty0 - kHF)) * kGW + (rx - (tx0 - kHG));
+        uint32_t acc = 0;
 #pragma unroll
-    for (int i = 1; i <= 3; ++i)
-      s = __fadd_rn(s, __fmul_rn(d[i], __fadd_rn(t[(size_t)reflect101(y + i, n) * n + x],
-                                                 t[(size_t)reflect101(y - i, n) * n + x])));
-  } else {
-    const bool fma = x < n - n % 4;
-    s = __fmul_rn(K.ks[3], t[(size_t)y * n + x]);
-#pragma unroll
-    for (int i = 1; i <= 3; ++i) {
-      const float v = __fadd_rn(t[(size_t)reflect101(y + i, n) * n + x], t[(size_t)reflect101(y - i, n) * n + x]);
-      s = fma ? __fmaf_rn(K.ks[3 + i], v, s) : __fadd_rn(s, __fmul_rn(K.ks[3 + i], v));
+        for (int k = 0; k < 13; ++k) acc += (uint32_t)c_gauss13[k] * t[(k - 6) * kGW];
+        G[gy * kGP + gx] = (uint8_t)min((acc + 32768u) >> 16, 255u);
+      }
     }
   }
-  const float r = fminf(fmaxf(rintf(s), 0.f), 255.f);
-  out[(size_t)y * n + x] = r > 30.f ? 255 : 0;
-}
+  __syncthreads();
 
-inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
+  // ---- Sobel second derivative, ksize 7, x 0.03: row pass R(gy, ex), then column pass + saturate + threshold
+  // -> E(ey, ex) for extended coordinates [t0 - 10, t0 + 74).  (rows of R are the G rows, which already hold
+  // G(reflect(row)); columns are read at reflect(ex) + tap through the same convention.)
+  {
+    const int row_vec_end = n - n % 32, col_vec_end = n - n % 4;
+    for (int gy = warp; gy < kGW; gy += kWarps)
+      for (int ex = lane; ex < kEW; ex += 32) {
+        const int rx = in_tile(reflect101(tx0 - kHE + ex, n), tx0, kHE);
+        const uint8_t *p = G + gy * kGP + (rx - 3 - (tx0 - kHG));
+        float s;
+        if (!a.rotated) {  // dx = 0, dy = 2: scaled smoothing along x, taps in order, FMA in the vector columns
+          const bool fma = rx < row_vec_end;
+          s = __fmul_rn(a.ks[0], (float)p[0]);
+#pragma unroll
+          for (int k = 1; k < 7; ++k) {
+            const float v = (float)p[k];
+            s = fma ? __fmaf_rn(a.ks[k], v, s) : __fadd_rn(s, __fmul_rn(a.ks[k], v));
+          }
+        } else {  // dx = 2, dy = 0: integer second derivative along x (exact)
+          const float d[7] = {1.f, 2.f, -1.f, -4.f, -1.f, 2.f, 1.f};
+          s = 0.f;
+#pragma unroll
+          for (int k = 0; k < 7; ++k) s = __fadd_rn(s, __fmul_rn(d[k], (float)p[k]));
+        }
+        R[gy * kEW + ex] = s;
+      }
+    __syncthreads();
+    for (int ey = warp; ey < kEW; ey += kWarps) {
+      const int ry = in_tile(reflect101(ty0 - kHE + ey, n), ty0, kHE);
+      for (int ex = lane; ex < kEW; ex += 32) {
+        const int rx = reflect101(tx0 - kHE + ex, n);
+        const float *t = R + (ry - (ty0 - kHG)) * kEW + ex;  // column ex already stands for reflect(ex)
+        float s;
+        if (!a.rotated) {
+          const float d[4] = {-4.f, -1.f, 2.f, 1.f};  // centre, +-1, +-2, +-3 of {1,2,-1,-4,-1,2,1}
+          s = __fmul_rn(d[0], t[0]);
+#pragma unroll
+          for (int j = 1; j <= 3; ++j) s = __fadd_rn(s, __fmul_rn(d[j], __fadd_rn(t[j * kEW], t[-j * kEW])));
+        } else {
+          const bool fma = rx < col_vec_end;
+          s = __fmul_rn(a.ks[3], t[0]);
+#pragma unroll
+          for (int j = 1; j <= 3; ++j) {
+            const float v = __fadd_rn(t[j * kEW], t[-j * kEW]);
+            s = fma ? __fmaf_rn(a.ks[3 + j], v, s) : __fadd_rn(s, __fmul_rn(a.ks[3 + j], v));
+          }
+        }
+        const float r = fminf(fmaxf(rintf(s), 0.f), 255.f);
+        E[ey * kEW + ex] = r > 30.f ? 255 : 0;  // F is dead since the first blur's row pass
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- second blur (fixed point) on E, then out = sat(score + 2 g)
+  {
+    uint16_t *B = reinterpret_cast<uint16_t *>(R);  // [kEW][kT] 8.8
+    for (int ey = warp; ey < kEW; ey += kWarps)
+      for (int ox = lane; ox < kT; ox += 32) {
+        const int rx = in_tile(reflect101(tx0 + ox, n), tx0, 0);  // columns past the image edge are never stored
+        const uint8_t *p = E + ey * kEW + (rx - tx0);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 21; ++k) acc += (uint32_t)c_gauss21[k] * p[k];
+        B[ey * kT + ox] = (uint16_t)acc;
+      }
+    __syncthreads();
+    for (int oy = warp; oy < kT; oy += kWarps) {
+      const int y = ty0 + oy;
+      if (y >= n) break;
+      for (int ox = lane; ox < kT; ox += 32) {
+        const int x = tx0 + ox;
+        if (x >= n) continue;
+        const uint16_t *t = B + oy * kT + ox;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 21; ++k) acc += (uint32_t)c_gauss21[k] * t[k * kT];
+        const uint32_t g = min((acc + 32768u) >> 16, 255u);
+        a.out[(size_t)y * n + x] = (uint8_t)min((uint32_t)S[oy * kT + ox] + 2u * g, 255u);
+      }
+    }
+  }
+}
 
 }  // namespace
-
-size_t score_scratch_bytes(int n) {
-  const size_t nn = (size_t)n * n;
-  return al((size_t)(n + 20) * n * 2) + al(nn * 4) + 2 * al(nn) + 256;
-}
 
 cudaError_t launch_score_preprocess(const ScoreLaunch &L, cudaStream_t stream, int *launches) {
   const int n = L.rect[2];
   if (launches) *launches = 0;
-  if (n <= 0) return cudaErrorInvalidValue;
-  Src s{L.frame, L.step, L.width, L.height, L.rotated};
-  SobelK K;
+  if (n <= 0 || L.rect[3] != n) return cudaErrorInvalidValue;
+  ScoreArgs a{};
+  a.frame = L.frame;
+  a.step = L.step;
+  a.w = L.width, a.h = L.height;
+  a.rotated = L.rotated ? 1 : 0;
+  a.rx = L.rect[0], a.ry = L.rect[1], a.n = n;
+  const int cols = L.rotated ? L.height : L.width, rows = L.rotated ? L.width : L.height;
+  a.submatrix = (n < cols || n < rows) ? 1 : 0;  // Mat::Mat(const Mat&, const Rect&) sets SUBMATRIX_FLAG iff smaller
   const float smooth[7] = {1, 6, 15, 20, 15, 6, 1};
   for (int i = 0; i < 7; ++i) {
     volatile float p = smooth[i] * 0.03f;  // float32 product, as Mat::operator*=(double) does for CV_32F
-    K.ks[i] = p;
+    a.ks[i] = p;
   }
-  const dim3 blk(128);
-  const dim3 g13((n + 127) / 128, n + 12), g21((n + 127) / 128, n + 20), gn((n + 127) / 128, n);
-  int n_launch = 6;
-  if (L.rotated && (size_t)(n + 12) * (n + 12) <= (size_t)n * n * 4) {
-    // (the float scratch is free until the Sobel pass)
-    uint8_t *roi = reinterpret_cast<uint8_t *>(L.f32);
-    const int m = n + 12;
-    rotcrop_kernel<<<dim3((m + 31) / 32, (m + 31) / 32), dim3(32, 8), 0, stream>>>(s, L.rect[0] - 6, L.rect[1] - 6, m, roi);
-    Src r{roi, (size_t)m, m, m, false};
-    gauss_rows_kernel<13><<<g13, blk, 0, stream>>>(r, 6, 6, n, n, L.rows16);
-    n_launch = 7;
-  } else {
-    gauss_rows_kernel<13><<<g13, blk, 0, stream>>>(s, L.rect[0], L.rect[1], n, n, L.rows16);
-  }
-  gauss_cols_kernel<13, false><<<gn, blk, 0, stream>>>(L.rows16, n, n, s, 0, 0, L.tmp8a);
-  sobel_rows_kernel<<<gn, blk, 0, stream>>>(L.tmp8a, n, L.rotated, K, L.f32);
-  sobel_cols_thresh_kernel<<<gn, blk, 0, stream>>>(L.f32, n, L.rotated, K, L.tmp8b);
-  Src e{L.tmp8b, (size_t)n, n, n, false};
-  gauss_rows_kernel<21><<<g21, blk, 0, stream>>>(e, 0, 0, n, n, L.rows16);
-  gauss_cols_kernel<21, true><<<gn, blk, 0, stream>>>(L.rows16, n, n, s, L.rect[0], L.rect[1], L.out);
-  if (launches) *launches = n_launch;
+  a.out = L.out;
+  cudaError_t e = cudaFuncSetAttribute(score_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+  if (e != cudaSuccess) return e;  // per device, cheap: set on every launch
+  const dim3 grid((n + kT - 1) / kT, (n + kT - 1) / kT);
+  score_tile_kernel<<<grid, kThreads, kSmemTotal, stream>>>(a);
+  if (launches) *launches = 1;
   return cudaGetLastError();
 }
 

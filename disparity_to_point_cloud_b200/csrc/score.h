@@ -12,13 +12,8 @@ struct ScoreLaunch {
   int width = 0, height = 0;
   bool rotated = false;  // true for score 2: the chain runs on rotateMat(frame) (90 deg clockwise, h cols x w rows)
   int rect[4] = {0, 0, 0, 0};  // cropToSquare rectangle {x, y, n, n} in the (rotated) frame
-  // scratch (device): rows16 >= (n + 20) * n * 2 bytes, f32 >= n * n * 4 bytes, tmp8a / tmp8b >= n * n bytes
-  uint16_t *rows16 = nullptr;
-  float *f32 = nullptr;
-  uint8_t *tmp8a = nullptr, *tmp8b = nullptr;
   uint8_t *out = nullptr;  // device, n x n dense: what the node caches as cropped_score_k_
 };
-size_t score_scratch_bytes(int n);  // total for rows16 + f32 + tmp8a + tmp8b, each 256-byte aligned
 cudaError_t launch_score_preprocess(const ScoreLaunch &L, cudaStream_t stream, int *launches);
 
 }  // namespace d2pc

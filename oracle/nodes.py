@@ -17,6 +17,24 @@ import numpy as np
 import oracle
 
 
+def grad_filter_np(d1, d2, s1, s2):
+    """gradFilter (src/depth_map_fusion.cpp:219-235) over arrays: numpy's float32 division is the same IEEE
+    operation as the C float division (tests/test_ref_compiled.py checks this function against the compiled
+    reference through d2pc_oracle_grad_filter_table)."""
+    d1, d2, s1, s2 = (np.asarray(v, dtype=np.int64) for v in (d1, d2, s1, s2))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = d1.astype(np.float32) / d2.astype(np.float32)
+    relative = rel.astype(np.float64)  # the comparisons promote the float to double (0.8, 1.25 are double literals)
+    take1 = (s1 < s2) & (s1 < 100) & (d1 < 230)
+    take2 = ~take1 & (s2 < s1) & (s2 < 100) & (d2 < 230)
+    avg = ~take1 & ~take2 & (0.8 < relative) & (relative < 1.25) & (s1 < 125.0) & (s2 < 125.0)
+    out = np.zeros(d1.shape, dtype=np.int64)
+    out[take1] = d1[take1]
+    out[take2] = d2[take2]
+    out[avg] = ((d1[avg] + d2[avg]).astype(np.float32) / np.float32(2.0)).astype(np.int64)  # float(d1 + d2) / 2.0, truncated
+    return out.astype(np.uint8)
+
+
 class FusionNodeOracle:
     def __init__(self, offset_x=0, offset_y=0, mode=0):
         self.ox, self.oy, self.mode = offset_x, offset_y, mode
@@ -75,12 +93,7 @@ class FusionNodeOracle:
         c1, c2 = self.s1.astype(np.int64), self.s2.astype(np.int64)
         fused = np.empty((n, n), dtype=np.uint8)
         if self.mode == 0:
-            # gradFilter per (d1, d2) at fixed scores is a table; group pixels by their score pair
-            keys = (c1 << 8) | c2
-            for key in np.unique(keys):
-                m = keys == key
-                tab = oracle.grad_filter_table(int(key) >> 8, int(key) & 255)
-                fused[m] = tab[a1[m], a2[m]]
+            fused = grad_filter_np(a1, a2, c1, c2)
         else:
             flat = [oracle.fuse_rule(self.mode, int(x), int(y), int(u), int(v))
                     for x, y, u, v in zip(a1.ravel(), a2.ravel(), c1.ravel(), c2.ravel())]

@@ -29,6 +29,26 @@ def test_score_chain_cv2_fixtures(ctx):
     ctx.set_tuning("offset_y", 15)
 
 
+@pytest.mark.parametrize("w,h,ox,oy", [(96, 96, 0, 0), (129, 160, 0, 0), (200, 65, 3, 0), (90, 40, -2, 1), (705, 64, 0, 0),
+                                       (300, 424, -7, 15), (64, 64, 0, 0), (128, 128, 1, 0)])
+def test_score_chain_tile_edges_and_blur_paths(ctx, w, h, ox, oy):
+    """Partial last tiles (n = 65, 129), a single tile, n smaller than the halos, and the two paths of the first
+    blur: a crop that is the whole frame (square frame, zero offsets) is not a submatrix and takes OpenCV's
+    fixed-point Gaussian, any smaller crop runs as sepFilter2D (float32)."""
+    ctx.set_tuning("offset_x", ox)
+    ctx.set_tuning("offset_y", oy)
+    try:
+        s1, s2 = _score_frame(h, w, 5), _score_frame(h, w, 6)
+        rc1, r1 = oracle.crop_to_square(w, h, ox, oy, oy)
+        rc2, r2 = oracle.crop_to_square(h, w, -ox, -oy, oy)
+        assert rc1 == 0 and rc2 == 0
+        assert_same_bits(ctx.preprocess_score(s1, 1), oracle.score_preprocess(s1, r1, False), "score 1")
+        assert_same_bits(ctx.preprocess_score(s2, 2), oracle.score_preprocess(oracle.rotate_cw(s2), r2, True), "score 2")
+    finally:
+        ctx.set_tuning("offset_x", -7)
+        ctx.set_tuning("offset_y", 15)
+
+
 def _score_frame(h, w, seed):
     rng = np.random.default_rng(seed)
     a = synth.s2_scene(h, w, seed)

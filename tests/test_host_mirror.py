@@ -100,3 +100,47 @@ def test_fusion_node_then_node1_config5(harness, tmp_path):
     assert fused_bin.read_bytes() == image_msg(fused, 2, 500)          # header of message 2 (:134-135)
     want = oracle.serialize_pointcloud2(oracle.disparity_cb_mono8(fused, q), seq=0, sec=2, nsec=500)
     assert cloud_bin.read_bytes() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w", [(300, 424), (480, 752)])
+def test_fusion_node_state_between_callbacks(harness, tmp_path, h, w):
+    """The state DepthMapFusion keeps between callbacks (src/depth_map_fusion.cpp:77, :113, :118-121):
+    DisparityCb2 before the caches are full publishes no fused map; two DisparityCb2 in a row -- the second merges
+    with score 1 = min(score 1, score 2) left behind by the first; a fresh MatchingScoreCb1 replaces it.  Every
+    message on all seven topics, in order, against oracle/nodes.py, which tests/test_ref_compiled.py pins to the
+    reference's own compiled class."""
+    from oracle import nodes
+    rng = np.random.default_rng(h + w)
+    seq = [2, 1, 3, 2, 4, 2, 2, 2, 3, 2, 4, 4, 2, 1, 2, 3]
+    o = nodes.FusionNodeOracle(-7, 15)   # launch/depth_map_fusion.launch
+    lines, want = [], []
+    for step, which in enumerate(seq):
+        img = _score_like(rng, h, w) if which in (3, 4) else synth.s2_scene(h, w, 100 + step)
+        p = tmp_path / f"m{step}.raw"
+        p.write_bytes(img.tobytes())
+        lines.append(f"{which} {p} {1000 + step} {17 * step}")
+        for topic, enc, arr, hdr in o.callback(which, img, (step, 1000 + step, 17 * step)):
+            want.append((topic, image_msg(np.ascontiguousarray(arr), hdr[1], hdr[2], seq=hdr[0])))
+    script, out = tmp_path / "script.txt", tmp_path / "log.bin"
+    script.write_text("\n".join(lines) + "\n")
+    subprocess.run([harness, "fusion-seq", os.path.join(ROOT, "launch", "depth_map_fusion.launch"), str(w), str(h),
+                    str(script), str(out)], check=True)
+    blob, got, i = out.read_bytes(), [], 0
+    while i < len(blob):
+        tl = struct.unpack_from("<I", blob, i)[0]
+        topic = blob[i + 4:i + 4 + tl].decode()
+        ml = struct.unpack_from("<I", blob, i + 4 + tl)[0]
+        got.append((topic, blob[i + 8 + tl:i + 8 + tl + ml]))
+        i += 8 + tl + ml
+    assert [t for t, _ in got] == [t for t, _ in want]
+    assert sum(t == "/fused_depth_map" for t, _ in got) == 6
+    for k, ((t, g_bytes), (_, w_bytes)) in enumerate(zip(got, want)):
+        assert g_bytes == w_bytes, (k, t)
+
+
+def _score_like(rng, h, w):
+    a = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    a[rng.integers(0, h, 6), :] = 250
+    a[:, rng.integers(0, w, 6)] = 3
+    return a

@@ -43,6 +43,14 @@ def test_grad_filter_exhaustive_against_the_reference(fusion, s1, s2):
     assert got.min() >= 0 and got.max() <= 255
 
 
+def test_numpy_grad_filter_is_the_c_oracle():
+    """oracle/nodes.py vectorises gradFilter in numpy; it must be the same function as the C table."""
+    dd1, dd2 = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    for s1, s2 in [(0, 0), (99, 100), (100, 99), (110, 110), (124, 124), (125, 124), (124, 125), (50, 200), (200, 50), (255, 0)]:
+        got = nodes.grad_filter_np(dd1, dd2, np.full_like(dd1, s1), np.full_like(dd1, s2))
+        assert np.array_equal(got, oracle.grad_filter_table(s1, s2)), (s1, s2)
+
+
 def test_alternate_rules_against_the_reference(fusion):
     """src/depth_map_fusion.cpp:169-217, modes 1..7 of d2pc_fuse_rule."""
     rng = np.random.default_rng(3)

@@ -10,6 +10,13 @@
 //       <cloud.bin> is given it is also fed to a Disparity2PCloud node whose /disparity is remapped to
 //       /fused_depth_map.  With <debug dir> the six debug topics are subscribed too and the last message of
 //       each is written there in wire format (cropped_depth_1.bin, ..., gradient.bin).
+//   d2pc_offline fusion-seq <fusion launch> <w> <h> <script.txt> <out.bin>
+//       An arbitrary callback sequence into one DepthMapFusion node: every script line is
+//       "<which> <frame.raw> <sec> <nsec>" with which = 1 /disparity_1, 2 /disparity_2, 3 /matching_score_1,
+//       4 /matching_score_2.  Every message the node publishes on any of its seven topics is appended to <out.bin>
+//       in publish order as {u32 topic length, topic, u32 wire length, ROS1 wire bytes}.  This is how the state the
+//       node keeps BETWEEN callbacks is tested (src/depth_map_fusion.cpp:77, :113, :118-121: after a fused publish the
+//       cached score 1 is min(score 1, score 2) until the next MatchingScoreCb1).
 //
 // It touches the GPU only through the C ABI (libd2pc_b200.so).
 #include <cstdio>
@@ -123,6 +130,41 @@ int main(int argc, char **argv) {
         if (debug.size() != 6) throw std::runtime_error("a debug topic was not published");
         for (const auto &kv : debug) write_file(std::string(argv[11]) + "/" + kv.first + ".bin", kv.second);
       }
+      return 0;
+    }
+    if (mode == "fusion-seq" && argc == 7) {
+      const uint32_t w = (uint32_t)std::atoi(argv[3]), h = (uint32_t)std::atoi(argv[4]);
+      d2pc_b200::Bus bus;
+      if (!bus.load_launch_file(argv[2])) throw std::runtime_error(std::string("cannot read ") + argv[2]);
+      depth_map_fusion::DepthMapFusion fusion(bus);
+      std::vector<uint8_t> log;
+      auto put32 = [&log](uint32_t v) {
+        for (int i = 0; i < 4; ++i) log.push_back((uint8_t)(v >> (8 * i)));
+      };
+      for (const char *t : {"cropped_depth_1", "cropped_depth_2", "cropped_score_1", "cropped_score_2", "combined_score",
+                            "gradient", "fused_depth_map"}) {
+        const std::string topic = std::string("/") + t;
+        bus.subscribe_image(topic, 5, [&log, &put32, topic](const sm::ImageConstPtr &m) {
+          const std::vector<uint8_t> wire = ros_lite::serialize(*m);
+          put32((uint32_t)topic.size());
+          log.insert(log.end(), topic.begin(), topic.end());
+          put32((uint32_t)wire.size());
+          log.insert(log.end(), wire.begin(), wire.end());
+        });
+      }
+      const char *inputs[5] = {"", "/disparity_1", "/disparity_2", "/matching_score_1", "/matching_score_2"};
+      std::ifstream script(argv[5]);
+      if (!script) throw std::runtime_error(std::string("cannot read ") + argv[5]);
+      int which;
+      std::string path;
+      uint32_t sec, nsec, seq = 0;
+      while (script >> which >> path >> sec >> nsec) {
+        if (which < 1 || which > 4) throw std::runtime_error("fusion-seq: which must be 1..4");
+        auto m = make_image(read_file(path, (size_t)w * h), w, h, sec, nsec);
+        m->header.seq = seq++;
+        bus.publish(bus.resolve(inputs[which]), m);
+      }
+      write_file(argv[6], log);
       return 0;
     }
     std::fprintf(stderr, "usage: see the header of tools/d2pc_offline.cpp\n");
