@@ -89,8 +89,18 @@ SYMBOLS = [
     ("d2pc_submit_mono8", C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     ("d2pc_submit_f32", C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     ("d2pc_wait", C.c_int, [_ctx, C.c_int, C.POINTER(Cloud)]),
+    ("d2pc_submit_mono8_into", C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                         C.c_size_t]),
+    ("d2pc_submit_f32_into", C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                       C.c_size_t]),
+    ("d2pc_process_mono8_into", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
+                                          C.POINTER(Cloud)]),
+    ("d2pc_process_f32_into", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
+                                        C.POINTER(Cloud)]),
     ("d2pc_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     ("d2pc_host_free", C.c_int, [C.c_void_p]),
+    ("d2pc_host_register", C.c_int, [C.c_void_p, C.c_size_t]),
+    ("d2pc_host_unregister", C.c_int, [C.c_void_p]),
     ("d2pc_process_stream", C.c_int, [_ctx, C.c_void_p, C.c_uint64, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32,
                                       C.c_uint32, C.c_uint32, CLOUD_SINK, C.c_void_p]),
     ("d2pc_reproject_f32_device", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t,
@@ -186,6 +196,23 @@ class PinnedArray:
             lib().d2pc_host_free(self._ptr)
             self._ptr = None
 
+
+class RegisteredArray:
+    """Page-locks an existing numpy array in place (d2pc_host_register) for the lifetime of this object."""
+
+    def __init__(self, array: np.ndarray):
+        assert array.flags["C_CONTIGUOUS"]
+        self.array = array
+        rc = lib().d2pc_host_register(array.ctypes.data, array.nbytes)
+        if rc:
+            raise D2pcError(rc, "d2pc_host_register")
+        self._live = True
+
+    def free(self):
+        if self._live:
+            lib().d2pc_host_unregister(self.array.ctypes.data)
+            self._live = False
+
     def __del__(self):  # pragma: no cover
         try:
             self.free()
@@ -207,13 +234,14 @@ class Context:
         rc = lib().d2pc_create(C.byref(cfg), device, C.byref(self._h))
         if rc:
             raise D2pcError(rc, "d2pc_create")
-        self._keep = []
+        self._keep = {}
 
     # -- lifecycle
     def close(self):
         if self._h:
             lib().d2pc_destroy(self._h)
             self._h = None
+        self._keep = {}
 
     def __enter__(self):
         return self
@@ -254,9 +282,23 @@ class Context:
     @staticmethod
     def _frame(img, dtype):
         a = np.asarray(img)
-        if a.dtype != dtype or a.ndim != 2 or a.strides[1] != a.itemsize:
+        # a row stride the C ABI cannot express (negative, or smaller than a row) is repacked, not passed on
+        if (a.dtype != dtype or a.ndim != 2 or a.strides[1] != a.itemsize or a.strides[0] < a.shape[1] * a.itemsize
+                or a.strides[0] > 0xFFFFFFFF):
             a = np.ascontiguousarray(a, dtype=dtype)
         return a
+
+    def process_into(self, frame, dst: np.ndarray) -> np.ndarray:
+        """DisparityCb with a caller-supplied destination (d2pc_process_*_into): the cloud bytes land in `dst`
+        (uint8, contiguous; DMA'd in place when it is PinnedArray / registered memory).  Returns dst[:n_bytes]."""
+        a = self._frame(frame, np.float32 if np.asarray(frame).dtype == np.float32 else np.uint8)
+        assert dst.dtype == np.uint8 and dst.flags["C_CONTIGUOUS"]
+        cl = Cloud()
+        fn = lib().d2pc_process_f32_into if a.dtype == np.float32 else lib().d2pc_process_mono8_into
+        self._check(fn(self._h, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], dst.ctypes.data, dst.size,
+                       C.byref(cl)), "d2pc_process_into")
+        self.last_cloud = cl
+        return dst.reshape(-1)[: cl.row_step * cl.height]
 
     def process_mono8(self, img, copy: bool = True) -> np.ndarray:
         """copy=False returns a view of the library-owned pinned buffer (valid until the next call)."""
@@ -275,10 +317,16 @@ class Context:
         self.last_cloud = cl
         return cl.bytes_view().copy() if copy else cl.bytes_view()
 
-    def submit(self, slot: int, frame):
+    def submit(self, slot: int, frame, dst: np.ndarray | None = None):
         a = np.asarray(frame)
-        assert a.ndim == 2 and a.strides[1] == a.itemsize
-        self._keep.append(a)
+        assert a.ndim == 2 and a.strides[1] == a.itemsize and a.strides[0] >= a.shape[1] * a.itemsize
+        self._keep[slot] = (a, dst)  # the frame (and destination) of a slot stay alive until it is waited on
+        if dst is not None:
+            assert dst.dtype == np.uint8 and dst.flags["C_CONTIGUOUS"] and a.dtype in (np.float32, np.uint8)
+            fn = lib().d2pc_submit_f32_into if a.dtype == np.float32 else lib().d2pc_submit_mono8_into
+            self._check(fn(self._h, slot, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], dst.ctypes.data,
+                           dst.size), "d2pc_submit_into")
+            return
         if a.dtype == np.float32:
             rc = lib().d2pc_submit_f32(self._h, slot, a.ctypes.data, a.shape[1], a.shape[0], a.strides[0])
         elif a.dtype == np.uint8:
@@ -289,8 +337,13 @@ class Context:
 
     def wait(self, slot: int) -> np.ndarray:
         cl = Cloud()
-        self._check(lib().d2pc_wait(self._h, slot, C.byref(cl)), "d2pc_wait")
+        try:
+            self._check(lib().d2pc_wait(self._h, slot, C.byref(cl)), "d2pc_wait")
+        finally:
+            kept = self._keep.pop(slot, None)
         self.last_cloud = cl
+        if kept is not None and kept[1] is not None:
+            return kept[1].reshape(-1)[: cl.row_step * cl.height]  # the caller's own buffer
         return cl.bytes_view().copy()
 
     def process_stream(self, frames: np.ndarray, collect: bool = True, sink=None, n_frames: int | None = None):
@@ -340,8 +393,14 @@ class Context:
         st = lib().d2pc_fuse_geometry(self._h, w, h, *(a.ctypes.data_as(_i32p) for a in (r1, r2, rc_, dims)))
         return st, tuple(map(int, r1)), tuple(map(int, r2)), tuple(map(int, rc_)), tuple(map(int, dims))
 
+    @staticmethod
+    def _same_shape(arrs, what):
+        if any(a.ndim != 2 or a.shape != arrs[0].shape for a in arrs):
+            raise ValueError(f"{what}: the input images must share one (H, W) shape, got {[a.shape for a in arrs]}")
+
     def fuse(self, d1, d2, s1, s2):
         arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (d1, d2, s1, s2)]
+        self._same_shape(arrs, "fuse")
         h, w = arrs[0].shape
         fused, combined = Image(), Image()
         self._check(lib().d2pc_fuse(self._h, *(a.ctypes.data for a in arrs), w, h, w, C.byref(fused),
@@ -363,7 +422,11 @@ class Context:
     def fuse_preprocessed(self, d1, d2, s1c, s2c):
         d1, d2 = (np.ascontiguousarray(a, dtype=np.uint8) for a in (d1, d2))
         s1c, s2c = (np.ascontiguousarray(a, dtype=np.uint8) for a in (s1c, s2c))
+        self._same_shape([d1, d2], "fuse_preprocessed")
         h, w = d1.shape
+        n = self.fuse_geometry(w, h)[4][0]
+        if s1c.shape != (n, n) or s2c.shape != (n, n):
+            raise ValueError(f"fuse_preprocessed: the score caches must be {n} x {n}, got {s1c.shape} and {s2c.shape}")
         fused, combined = Image(), Image()
         self._check(lib().d2pc_fuse_preprocessed(self._h, d1.ctypes.data, d2.ctypes.data, s1c.ctypes.data,
                                                  s2c.ctypes.data, w, h, w, C.byref(fused), C.byref(combined)),
@@ -383,6 +446,7 @@ class Context:
 
     def fuse_then_process(self, d1, d2, s1, s2) -> np.ndarray:
         arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (d1, d2, s1, s2)]
+        self._same_shape(arrs, "fuse_then_process")
         h, w = arrs[0].shape
         cl = Cloud()
         self._check(lib().d2pc_fuse_then_process(self._h, *(a.ctypes.data for a in arrs), w, h, w, C.byref(cl)),

@@ -12,6 +12,7 @@
 #include "../../include/d2pc_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -52,6 +53,10 @@ struct Slot {
   uint32_t width = 0, height = 0;
   uint64_t n_points = 0;
   bool compact = false;
+  // caller-supplied destination of this submission (d2pc_submit_*_into); nullptr = library-owned h_out
+  uint8_t *user_dst = nullptr;
+  size_t user_cap = 0;
+  bool user_pinned = false;
 };
 
 }  // namespace
@@ -83,10 +88,16 @@ struct d2pc_ctx {
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0, median_variant = 0;
   bool force_scalar = false, force_generic = false;
   int compact_variant = 0, exact_variant = 0, pipe_stages = 0, pipe_producers = 0, pipe_consumers = 0, prefetch_dist = 0;
-  std::vector<std::pair<uintptr_t, bool>> pin_cache;  // host pointer -> cudaHostAlloc'ed?
+  std::vector<std::pair<uintptr_t, bool>> pin_cache;  // host pointer -> pinned (cudaHostAlloc / cudaHostRegister)?
+  uint64_t pin_cache_gen = 0;                         // value of g_host_gen the cache was filled under
 };
 
 namespace {
+
+// bumped whenever pinned host memory is released (d2pc_host_free / d2pc_host_unregister): a context's
+// pointer -> "is pinned" cache is only trusted while this has not moved, so a freed and re-allocated address is
+// looked up again instead of answered from memory.
+std::atomic<uint64_t> g_host_gen{1};
 
 int cuda_fail(d2pc_ctx *ctx, cudaError_t e, const char *what) {
   if (ctx) {
@@ -111,7 +122,9 @@ int grow_dev(d2pc_ctx *ctx, DevBuf &b, size_t bytes, bool zero = false) {
   b.cap = 0;
   const size_t cap = align_up(bytes, 1 << 16);
   CU(ctx, cudaMalloc(&b.p, cap));
-  if (zero) CU(ctx, cudaMemset(b.p, 0, cap));
+  // cleared on the compute stream: every kernel that reads the buffer is enqueued there later, so the clear is
+  // ordered before it (a legacy-stream cudaMemset is not ordered with cudaStreamNonBlocking streams)
+  if (zero) CU(ctx, cudaMemsetAsync(b.p, 0, cap, ctx->s_compute));
   b.cap = cap;
   return D2PC_OK;
 }
@@ -145,8 +158,8 @@ uint32_t next_epoch(d2pc_ctx *ctx) {
     ctx->epoch = 1;
     cudaDeviceSynchronize();
     for (auto &s : ctx->slots)
-      if (s.d_scratch.p) cudaMemset(s.d_scratch.p, 0, s.d_scratch.cap);
-    if (ctx->d_scratch.p) cudaMemset(ctx->d_scratch.p, 0, ctx->d_scratch.cap);
+      if (s.d_scratch.p) cudaMemsetAsync(s.d_scratch.p, 0, s.d_scratch.cap, ctx->s_compute);
+    if (ctx->d_scratch.p) cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, ctx->s_compute);
   }
   return ctx->epoch;
 }
@@ -179,6 +192,23 @@ bool is_pinned_host(const void *p) {
     return false;
   }
   return at.type == cudaMemoryTypeHost;
+}
+
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Looked up once per distinct buffer (a
+// subscriber reuses a handful of message buffers); the cache is dropped when pinned memory has been released since.
+bool lookup_pinned(d2pc_ctx *ctx, const void *p) {
+  const uint64_t gen = g_host_gen.load(std::memory_order_acquire);
+  if (ctx->pin_cache_gen != gen) {
+    ctx->pin_cache.clear();
+    ctx->pin_cache_gen = gen;
+  }
+  const uintptr_t p0 = reinterpret_cast<uintptr_t>(p);
+  for (const auto &e : ctx->pin_cache)
+    if (e.first == p0) return e.second;
+  const bool pinned = is_pinned_host(p);
+  if (ctx->pin_cache.size() >= 64) ctx->pin_cache.clear();
+  ctx->pin_cache.emplace_back(p0, pinned);
+  return pinned;
 }
 
 // Enqueue [median] + reproject for one frame batch already on the device.
@@ -265,7 +295,8 @@ int slot_wait_idle(d2pc_ctx *ctx, Slot &s) {
   return D2PC_OK;
 }
 
-int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_t h, uint32_t step, bool is_f32) {
+int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_t h, uint32_t step, bool is_f32,
+                  uint8_t *user_dst = nullptr, size_t user_cap = 0) {
   if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return D2PC_ERR_INVALID_ARG;
   const int esz = is_f32 ? 4 : 1;
   int rc = check_frame(ctx, data, w, h, step, esz);
@@ -280,10 +311,12 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   const size_t d_pitch = (row_bytes % 16 == 0) ? row_bytes : align_up(row_bytes, kAlign);
   const uint64_t n = crop_points(w, h, ctx->cfg.border);
   const bool compact = ctx->cfg.filter_mode == D2PC_FILTER_CROP_FINITE;
+  if (user_dst && !compact && user_cap < n * 16) return D2PC_ERR_BUFFER_TOO_SMALL;
+  const bool user_pinned = user_dst && reinterpret_cast<uintptr_t>(user_dst) % 16 == 0 && lookup_pinned(ctx, user_dst);
   if ((rc = grow_dev(ctx, s.d_in, d_pitch * h))) return rc;
   if (!is_f32 && ctx->cfg.median_ksize > 1 && (rc = grow_dev(ctx, s.d_med, d_pitch * h))) return rc;
   if ((rc = grow_dev(ctx, s.d_out, n * 16 + 16))) return rc;
-  if ((rc = grow_pin(ctx, s.h_out, n * 16 + 16))) return rc;
+  if (!user_pinned && (rc = grow_pin(ctx, s.h_out, n * 16 + 16))) return rc;
   if (compact && ((rc = grow_dev(ctx, s.d_scratch, reproject_scratch_bytes(1, w, h, ctx->cfg.border), true)) ||
                   (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(w, h))) ||
                   (rc = grow_dev(ctx, s.d_cells, reproject_cells_bytes(1, w, h, ctx->cfg.border)))))
@@ -292,19 +325,7 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   // ---- H2D (stream 1).  Pinned caller memory is DMA'd in place; pageable memory is staged.
   const void *src = data;
   size_t src_pitch = step;
-  // pinned-ness is looked up once per distinct buffer (a subscriber reuses a handful of message buffers)
-  bool pinned = false;
-  {
-    const uintptr_t p0 = reinterpret_cast<uintptr_t>(data);
-    bool known = false;
-    for (const auto &e : ctx->pin_cache)
-      if (e.first == p0) known = true, pinned = e.second;
-    if (!known) {
-      pinned = is_pinned_host(data);
-      if (ctx->pin_cache.size() >= 64) ctx->pin_cache.clear();
-      ctx->pin_cache.emplace_back(p0, pinned);
-    }
-  }
+  const bool pinned = lookup_pinned(ctx, data);
   if (!pinned) {
     if ((rc = grow_pin(ctx, s.h_in, row_bytes * h))) return rc;
     if (step == row_bytes) {
@@ -335,7 +356,8 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
     // the kept count decides how many bytes travel: fetch it, the payload copy is issued in d2pc_wait
     CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
   } else if (n) {
-    CU(ctx, cudaMemcpyAsync(s.h_out.p, s.d_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    // a page-locked caller buffer receives the cloud by DMA directly; a pageable one is filled from h_out in wait
+    CU(ctx, cudaMemcpyAsync(user_pinned ? user_dst : s.h_out.p, s.d_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
   }
   CU(ctx, cudaEventRecord(s.ev_d2h, ctx->s_d2h));
   s.pending = true;
@@ -343,6 +365,9 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   s.height = h;
   s.n_points = n;
   s.compact = compact;
+  s.user_dst = user_dst;
+  s.user_cap = user_cap;
+  s.user_pinned = user_pinned;
   return D2PC_OK;
 }
 
@@ -472,7 +497,7 @@ int d2pc_create(const d2pc_config *cfg, int device, d2pc_ctx **out) {
       return fail(D2PC_ERR_CUDA);
     if (cudaMalloc(&s.d_count, 64) != cudaSuccess) return fail(D2PC_ERR_NOMEM);
     if (cudaHostAlloc(&s.h_count, 64, cudaHostAllocDefault) != cudaSuccess) return fail(D2PC_ERR_NOMEM);
-    cudaMemset(s.d_count, 0, 64);
+    cudaMemsetAsync(s.d_count, 0, 64, ctx->s_compute);
   }
   rc = d2pc_q_from_intrinsics(c.fx, c.fy, c.cx, c.cy, c.baseline, c.rect_width, c.rect_height, ctx->q);
   if (rc) return fail(rc);
@@ -603,17 +628,44 @@ int d2pc_wait(d2pc_ctx *ctx, int slot, d2pc_cloud *out) {
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaEventSynchronize(s.ev_d2h));
   uint64_t n = s.n_points;
+  uint8_t *dst = s.user_pinned ? s.user_dst : s.h_out.p;  // where the DMA lands
   if (s.compact) {
     n = s.n_points ? s.h_count[0] : 0;
+    if (s.user_dst && s.user_cap < n * 16) {
+      s.pending = false;
+      return D2PC_ERR_BUFFER_TOO_SMALL;
+    }
     if (n) {
-      CU(ctx, cudaMemcpyAsync(s.h_out.p, s.d_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
+      CU(ctx, cudaMemcpyAsync(dst, s.d_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
       CU(ctx, cudaStreamSynchronize(ctx->s_d2h));
     }
   }
+  if (s.user_dst && !s.user_pinned && n) memcpy(s.user_dst, s.h_out.p, n * 16);
   s.pending = false;
   if (ctx->cfg.verbose) printf("Cloud size: %llu\n", (unsigned long long)n);  // cpp:82
-  if (out) fill_cloud(ctx, s.h_out.p, n, s.compact, out);
+  if (out) fill_cloud(ctx, s.user_dst ? s.user_dst : s.h_out.p, n, s.compact, out);
   return D2PC_OK;
+}
+
+int d2pc_submit_mono8_into(d2pc_ctx *ctx, int slot, const uint8_t *data, uint32_t w, uint32_t h, uint32_t step,
+                           uint8_t *dst, size_t cap) {
+  if (!dst) return D2PC_ERR_INVALID_ARG;
+  return submit_common(ctx, slot, data, w, h, step, false, dst, cap);
+}
+int d2pc_submit_f32_into(d2pc_ctx *ctx, int slot, const float *disp, uint32_t w, uint32_t h, uint32_t step,
+                         uint8_t *dst, size_t cap) {
+  if (!dst) return D2PC_ERR_INVALID_ARG;
+  return submit_common(ctx, slot, disp, w, h, step, true, dst, cap);
+}
+int d2pc_process_mono8_into(d2pc_ctx *ctx, const uint8_t *data, uint32_t w, uint32_t h, uint32_t step, uint8_t *dst,
+                            size_t cap, d2pc_cloud *out) {
+  int rc = d2pc_submit_mono8_into(ctx, 0, data, w, h, step, dst, cap);
+  return rc ? rc : d2pc_wait(ctx, 0, out);
+}
+int d2pc_process_f32_into(d2pc_ctx *ctx, const float *disp, uint32_t w, uint32_t h, uint32_t step, uint8_t *dst,
+                          size_t cap, d2pc_cloud *out) {
+  int rc = d2pc_submit_f32_into(ctx, 0, disp, w, h, step, dst, cap);
+  return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 
 int d2pc_process_mono8(d2pc_ctx *ctx, const uint8_t *data, uint32_t w, uint32_t h, uint32_t step, d2pc_cloud *out) {
@@ -639,7 +691,27 @@ int d2pc_host_alloc(void **ptr, size_t bytes) {
 }
 int d2pc_host_free(void *ptr) {
   if (!ptr) return D2PC_OK;
+  g_host_gen.fetch_add(1, std::memory_order_acq_rel);  // contexts forget what they knew about this address
   return cudaFreeHost(ptr) == cudaSuccess ? D2PC_OK : D2PC_ERR_CUDA;
+}
+int d2pc_host_register(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return D2PC_ERR_INVALID_ARG;
+  g_host_gen.fetch_add(1, std::memory_order_acq_rel);  // a pageable address becomes pinned: cached answers are stale
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? D2PC_ERR_NOMEM : D2PC_ERR_CUDA;
+  }
+  return D2PC_OK;
+}
+int d2pc_host_unregister(void *ptr) {
+  if (!ptr) return D2PC_OK;
+  g_host_gen.fetch_add(1, std::memory_order_acq_rel);
+  if (cudaHostUnregister(ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return D2PC_ERR_CUDA;
+  }
+  return D2PC_OK;
 }
 
 int d2pc_process_stream(d2pc_ctx *ctx, const void *frames, uint64_t n_frames, size_t frame_stride, uint64_t ring_len,
@@ -712,7 +784,7 @@ static int reproject_device_common(d2pc_ctx *ctx, const void *d_in, bool is_f32,
 int d2pc_reproject_f32_device(d2pc_ctx *ctx, const float *d_disp, uint32_t n_frames, uint32_t w, uint32_t h,
                               size_t step, size_t frame_stride, uint8_t *d_points, size_t points_stride,
                               uint32_t *d_counts) {
-  if (step % 4 || frame_stride % 4) return D2PC_ERR_BAD_DIMS;
+  if (step % 4 || frame_stride % 4 || reinterpret_cast<uintptr_t>(d_disp) % 4) return D2PC_ERR_BAD_DIMS;
   return reproject_device_common(ctx, d_disp, true, n_frames, w, h, step, frame_stride, d_points, points_stride,
                                  d_counts);
 }

@@ -108,7 +108,8 @@ typedef struct d2pc_point_field {
 
 /* The sensor_msgs/PointCloud2 payload DisparityCb publishes
  * (src/disparity_to_point_cloud.cpp:79-90).  `data` is library-owned pinned
- * host memory, valid until the next call that uses the same slot. */
+ * host memory, valid until the next call that uses the same slot -- or the
+ * caller's own buffer when one of the *_into entry points was used. */
 typedef struct d2pc_cloud {
   const uint8_t *data; /* width * 16 bytes: {f32 x, f32 y, f32 z, f32 1.0} */
   uint32_t height;     /* 1 */
@@ -170,9 +171,30 @@ int d2pc_submit_mono8(d2pc_ctx *ctx, int slot, const uint8_t *data, uint32_t wid
 int d2pc_submit_f32(d2pc_ctx *ctx, int slot, const float *disp, uint32_t width, uint32_t height, uint32_t step);
 int d2pc_wait(d2pc_ctx *ctx, int slot, d2pc_cloud *out);
 
-/* Pinned host memory for inputs the caller wants DMA'd without staging. */
+/* The same calls with a CALLER-SUPPLIED destination for the cloud (SURVEY.md 8(b) "Ownership"): what
+ * pcl::toROSMsg's memcpy into PointCloud2.data does in the reference (src/disparity_to_point_cloud.cpp:84-85)
+ * becomes the device-to-host copy itself.  `dst` must hold the whole cloud (16 bytes per point; `cap` bytes are
+ * available, D2PC_ERR_BUFFER_TOO_SMALL otherwise -- in CROP mode at submit, in CROP_FINITE mode, where the count
+ * is only known afterwards, at wait).  When `dst` is page-locked (d2pc_host_alloc, or any buffer passed through
+ * d2pc_host_register, e.g. the storage of a message's data vector) and 16-byte aligned the DMA engine writes
+ * straight into it; a pageable `dst` is filled from the library's pinned buffer when the slot is waited on.
+ * `dst` must stay valid until d2pc_wait(slot) returns; the cloud returned by d2pc_wait then points at `dst`. */
+int d2pc_submit_mono8_into(d2pc_ctx *ctx, int slot, const uint8_t *data, uint32_t width, uint32_t height,
+                           uint32_t step, uint8_t *dst, size_t cap);
+int d2pc_submit_f32_into(d2pc_ctx *ctx, int slot, const float *disp, uint32_t width, uint32_t height, uint32_t step,
+                         uint8_t *dst, size_t cap);
+int d2pc_process_mono8_into(d2pc_ctx *ctx, const uint8_t *data, uint32_t width, uint32_t height, uint32_t step,
+                            uint8_t *dst, size_t cap, d2pc_cloud *out);
+int d2pc_process_f32_into(d2pc_ctx *ctx, const float *disp, uint32_t width, uint32_t height, uint32_t step,
+                          uint8_t *dst, size_t cap, d2pc_cloud *out);
+
+/* Pinned host memory for buffers the caller wants DMA'd without staging: allocate it here, or page-lock memory
+ * the caller already owns (cudaHostRegister; costs about as much as touching every page once, so register
+ * long-lived buffers, not one per message). */
 int d2pc_host_alloc(void **ptr, size_t bytes);
 int d2pc_host_free(void *ptr);
+int d2pc_host_register(void *ptr, size_t bytes);
+int d2pc_host_unregister(void *ptr);
 
 /* Streams `n_frames` same-sized frames through the slot pipeline and hands every finished cloud to `sink` in
  * frame order (sink may be NULL: the clouds are then produced and dropped).  Frame i is read from

@@ -166,6 +166,26 @@ class Disparity2PCloud {
   double base_line_ = 0.09;  // Omni-stereo
   double Q_[16];
   d2pc_ctx *ctx_ = nullptr;
+  // The published message is a member, not a local as in the reference (cpp:83): the storage of its data vector
+  // is page-locked once (d2pc_host_register) and the library DMAs every cloud straight into it, so the memcpy
+  // of pcl::toROSMsg (cpp:84-85) has no counterpart here.
+  sensor_msgs::PointCloud2 output_;
+  uint8_t *registered_ = nullptr;
+  int border_ = 40;  // cpp:70,72
+
+  // make output_.data hold `bytes` bytes in page-locked storage without touching bytes it already has
+  void reserve_output(size_t bytes) {
+    if (output_.data.capacity() < bytes || output_.data.data() != registered_) {
+      if (registered_) d2pc_host_unregister(registered_);
+      registered_ = nullptr;
+      output_.data.clear();
+      output_.data.reserve(bytes + bytes / 4 + 4096);
+      output_.data.resize(bytes);
+      if (d2pc_host_register(output_.data.data(), output_.data.capacity()) == D2PC_OK) registered_ = output_.data.data();
+    } else if (output_.data.size() != bytes) {
+      output_.data.resize(bytes);  // capacity suffices: the storage (and its registration) stays
+    }
+  }
 
  public:
   explicit Disparity2PCloud(d2pc_b200::Bus &nh, int device = 0, bool verbose = false) : nh_(nh) {
@@ -184,10 +204,14 @@ class Disparity2PCloud {
     d2pc_config_default(&cfg);
     cfg.fx = fx_, cfg.fy = fy_, cfg.cx = cx_, cfg.cy = cy_, cfg.baseline = base_line_;
     cfg.verbose = verbose ? 1 : 0;
+    border_ = cfg.border;
     d2pc_b200::check(d2pc_create(&cfg, device, &ctx_), "d2pc_create");
     d2pc_get_q(ctx_, Q_);
   }
-  ~Disparity2PCloud() { d2pc_destroy(ctx_); }
+  ~Disparity2PCloud() {
+    d2pc_destroy(ctx_);  // waits for the device: nothing writes into output_ any more
+    if (registered_) d2pc_host_unregister(registered_);
+  }
   Disparity2PCloud(const Disparity2PCloud &) = delete;
   Disparity2PCloud &operator=(const Disparity2PCloud &) = delete;
 
@@ -197,12 +221,18 @@ class Disparity2PCloud {
   // src/disparity_to_point_cloud.cpp:46-92
   void DisparityCb(const sensor_msgs::ImageConstPtr &msg) {
     d2pc_b200::require_mono8(*msg);
+    const long cw = static_cast<long>(msg->width) - 2L * border_, ch = static_cast<long>(msg->height) - 2L * border_;
+    reserve_output(cw > 0 && ch > 0 ? static_cast<size_t>(cw) * static_cast<size_t>(ch) * 16 : 0);
     d2pc_cloud cloud;
-    d2pc_b200::check(d2pc_process_mono8(ctx_, msg->data.data(), msg->width, msg->height, msg->step, &cloud),
-                     "d2pc_process_mono8", ctx_);
-    sensor_msgs::PointCloud2 output;  // pcl::toROSMsg(*cloud, output), cpp:84-85
+    uint8_t dummy[16];
+    uint8_t *dst = output_.data.empty() ? dummy : output_.data.data();
+    d2pc_b200::check(d2pc_process_mono8_into(ctx_, msg->data.data(), msg->width, msg->height, msg->step, dst,
+                                             output_.data.size(), &cloud),
+                     "d2pc_process_mono8_into", ctx_);
+    sensor_msgs::PointCloud2 &output = output_;  // pcl::toROSMsg(*cloud, output), cpp:84-85 -- the bytes are already there
     output.height = cloud.height;
     output.width = cloud.width;
+    output.fields.clear();
     for (uint32_t i = 0; i < cloud.n_fields; ++i) {
       sensor_msgs::PointField f;
       f.name = cloud.fields[i].name;
@@ -215,7 +245,8 @@ class Disparity2PCloud {
     output.point_step = cloud.point_step;
     output.row_step = cloud.row_step;
     output.is_dense = cloud.is_dense;
-    output.data.assign(cloud.data, cloud.data + static_cast<size_t>(cloud.row_step) * cloud.height);
+    // CROP_FINITE keeps fewer points than the crop holds: shrink the view, never the storage
+    output.data.resize(static_cast<size_t>(cloud.row_step) * cloud.height);
     output.header.stamp = msg->header.stamp;             // cpp:87
     output.header.frame_id = "/camera_optical_frame";    // cpp:89
     nh_.publish(p_cloud_topic_, output);                 // cpp:90

@@ -1,5 +1,6 @@
 // ROS1 shim: the reference's depth_map_fusion_node with the per-pixel merge on the GPU (libd2pc_b200.so).
-// Built only where catkin/roscpp exist; NOT built in the development image.
+// Built with catkin where roscpp exists (ros1_shim/package.xml, CMakeLists.txt); in the development image it is
+// compiled and linked against the API stand-ins of tests/ros_stubs/ (tests/test_ros1_shim.py).
 // Subscriptions, the /fused_depth_map publisher, the offset_x / offset_y parameters follow
 // include/disparity_to_point_cloud/depth_map_fusion.hpp:97-124, so launch/depth_map_fusion.launch works unchanged.
 // Score frames are preprocessed on the GPU as they arrive (Gaussian / Sobel / threshold / Gaussian chain of

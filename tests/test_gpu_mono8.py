@@ -148,6 +148,62 @@ def test_slot_pipeline_and_stream(ctx, q):
     pin.free()
 
 
+def test_caller_supplied_destination(ctx, q):
+    """d2pc_process_*_into / d2pc_submit_*_into (SURVEY 8(b) Ownership): the cloud lands in the caller's buffer --
+    by DMA when it is page-locked (d2pc_host_alloc or d2pc_host_register), through the library's pinned buffer
+    when it is pageable -- and nothing is written past the cloud."""
+    import ctypes as C
+    import disparity_to_point_cloud_b200 as d2pc
+    h, w = 480, 752
+    img = synth.s2_scene(h, w, 60)
+    want = oracle.disparity_cb_mono8(img, q)
+    nb = want.size
+    pin = d2pc.PinnedArray((nb + 64,), np.uint8)
+    own = np.empty(nb + 64, np.uint8)
+    reg = d2pc.RegisteredArray(np.empty(nb + 64, np.uint8))
+    try:
+        for name, dst in (("pinned", pin.array), ("pageable", own), ("registered", reg.array)):
+            dst[:] = 0xAB
+            got = ctx.process_into(img, dst)
+            assert got.ctypes.data == dst.ctypes.data and got.size == nb
+            assert ctx.last_cloud.width == nb // 16 and C.addressof(ctx.last_cloud.data.contents) == dst.ctypes.data
+            assert_same_bits(got, want, name)
+            assert (dst[nb:] == 0xAB).all(), name
+        d = synth.s3_float(h, w, 61)
+        assert_same_bits(ctx.process_into(d, pin.array), oracle.disparity_cb_f32(d, q), "float entry")
+        # too small: refused at submit in CROP mode, nothing written
+        small = np.full(nb - 16, 0xCD, np.uint8)
+        with pytest.raises(d2pc.D2pcError) as e:
+            ctx.process_into(img, small)
+        assert e.value.status == -9 and (small == 0xCD).all()
+        # slots: two frames in flight into two caller buffers, waited out of order
+        a, b = synth.s2_scene(h, w, 62), synth.s1_uniform(h, w, 63)
+        da, db = pin.array[:nb], reg.array[:nb]
+        ctx.submit(0, a, dst=da)
+        ctx.submit(1, b, dst=db)
+        assert_same_bits(ctx.wait(1), oracle.disparity_cb_mono8(b, q), "slot 1")
+        assert_same_bits(ctx.wait(0), oracle.disparity_cb_mono8(a, q), "slot 0")
+        # CROP_FINITE: the count is only known afterwards; a buffer that holds the kept points is enough
+        ctx.set_filter_mode(d2pc.FILTER_CROP_FINITE)
+        try:
+            kept = oracle.filter_finite(want)
+            assert 0 < kept.size < nb
+            own[:] = 0xAB
+            got = ctx.process_into(img, own[:kept.size])
+            assert_same_bits(got, kept, "compacted into a caller buffer")
+            assert (own[kept.size:] == 0xAB).all()
+            with pytest.raises(d2pc.D2pcError) as e:
+                ctx.process_into(img, own[:kept.size - 16])
+            assert e.value.status == -9
+        finally:
+            ctx.set_filter_mode(d2pc.FILTER_CROP)
+        # the library-owned path still works after caller-owned submissions on the same slot
+        assert_same_bits(ctx.process_mono8(img), want, "library-owned after into")
+    finally:
+        pin.free()
+        reg.free()
+
+
 def test_float_stream_matches_single_calls(ctx, q):
     f, h, w = 7, 300, 420
     frames = np.stack([synth.s4_stress(h, w, 80 + i) for i in range(f)])
@@ -175,3 +231,7 @@ def test_bad_arguments(ctx):
     assert L.d2pc_process_mono8(ctx._h, img.ctypes.data, 0, 10, 10, C.byref(cl)) == -3
     assert L.d2pc_submit_mono8(ctx._h, 99, img.ctypes.data, 10, 10, 10) == -1
     assert L.d2pc_set_filter_mode(ctx._h, 7) == -1
+    assert L.d2pc_process_mono8_into(ctx._h, img.ctypes.data, 10, 10, 10, None, 0, C.byref(cl)) == -1
+    assert L.d2pc_host_register(None, 16) == -1
+    # d2pc_reproject_f32_device: a float pointer that is not 4-byte aligned is refused, not dereferenced
+    assert L.d2pc_reproject_f32_device(ctx._h, 0x1001, 1, 100, 100, 400, 40000, 0x2000, 0, None) == -3

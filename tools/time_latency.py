@@ -30,6 +30,20 @@ with d2pc.Context() as ctx:
         d = synth.s3_float(h, w, 1)
         m8 = lat(lambda: ctx.process_mono8(img, copy=False))
         f32 = lat(lambda: ctx.process_f32(d, copy=False))
+        # the message a subscriber publishes: library-owned cloud + the copy into the message (what pcl::toROSMsg
+        # does in the reference, cpp:84-85) versus the cloud DMA'd straight into a page-locked message buffer
+        n = oracle.n_points(w, h) * 16
+        msg = np.empty(n, np.uint8)
+
+        def with_copy():
+            msg[:] = ctx.process_mono8(img, copy=False)
+
+        reg = d2pc.RegisteredArray(np.empty(n, np.uint8))
+        cp = lat(with_copy)
+        into = lat(lambda: ctx.process_into(img, reg.array))
+        reg.free()
+        print(f"{w}x{h}: mono8 -> message buffer: library cloud + memcpy {cp[0]:.0f} us (p99 {cp[1]:.0f}), "
+              f"d2pc_process_mono8_into a registered buffer {into[0]:.0f} us (p99 {into[1]:.0f})", flush=True)
         t0 = time.perf_counter()
         for _ in range(3):
             oracle.disparity_cb_mono8(img, q)
