@@ -1,24 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- disparity -> PointCloud2 throughput (BASELINE.json's metric) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
     (N > 1 is launched by the driver under torch.distributed.run, one rank per GPU)
 
-Workload (BASELINE.json configs[3], the one the 1/2/4/8-GPU metric is quoted on): 3840x2160 float32 disparity
-frames (S3 distribution) through the reference's reprojection path (src/disparity_to_point_cloud.cpp:63-85):
-reproject with Q -> 40-px crop -> pack {x,y,z,1.0f}.  A step is one pass over a batch of 1024 frames PER GPU
-(frames are independent, so ranks shard them with no collective: weak scaling).
+--config selects the BASELINE.json workload (numbered as SURVEY.md section 8 numbers them, = configs[N-1]); every
+config prints ONE JSON line with the same keys (value, e2e, roofline, cpu_baseline, clocks ...):
 
-  value      Mpixel/s of input disparity, kernel-only: inputs resident in HBM in a ring of frame slots that is
-             larger than L2 (so every launch streams from HBM), CUDA events on the launching stream.
-  e2e        same metric through the C ABI's host entry (d2pc_process_stream): pinned host frames, H2D, kernel,
-             D2H of every PointCloud2 payload, three streams / three slots overlapped.  Wall clock bracketed by
-             device synchronisation (the work spans three streams), max over ranks.
-  roofline   algorithmic bytes (20 B per kept point) / measured kernel time vs measured HBM peak.
+  4 (default, the headline the 1/2/4/8-GPU metric is quoted on): 3840x2160 float32 disparity frames (S3) through
+    the reference's reprojection path (src/disparity_to_point_cloud.cpp:63-85): reproject with Q -> 40-px crop ->
+    pack {x,y,z,1.0f}.  A step is 1024 frames PER GPU (weak scaling; --scaling strong shards 1024 in total).
+  3: 1280x720 float32, a step is one batch of 64 frames (kernel-only is what BASELINE quotes; e2e reported too).
+  2: 752x480 mono8 stream (S2 scene), the whole DisparityCb (cpp:46-92: median 11 -> x1/8 -> reproject -> crop ->
+     pack); a step is 1000 frames.
+  5: depth_map_fusion: four 1280x720 mono8 maps per frame set -> MatchingScoreCb1/2, DisparityCb1/2,
+     publishFusedDepthMap (src/depth_map_fusion.cpp:46-136) -> DisparityCb on the fused 665x665 map; a step is 256
+     frame sets PER GPU, frame sets sharded over the GPUs.
+
+  value      Mpixel/s of input pixels, kernel-only: inputs resident in HBM in a ring larger than L2 (every launch
+             streams from HBM), CUDA events on the launching stream, max over ranks.
+  e2e        the same metric through the C ABI's host entry (d2pc_process_stream / d2pc_process_fusion_stream):
+             pinned host frames, H2D, kernels, D2H of every PointCloud2 payload, three streams / slots overlapped.
+             Wall clock bracketed by device synchronisation (the work spans three streams), max over ranks.
+             e2e.ceiling_gbs is the raw rate of plain pinned cudaMemcpyAsync traffic of the same shape (same bytes
+             per frame each way, all ranks at once): what the host / PCIe path can carry with no kernels at all.
+  roofline   algorithmic bytes / measured kernel time vs the measured HBM peak.
   cpu_baseline  the CPU oracle port of the same path on a bounded sample, timed on this host (N=1, rank 0).
 
---impl reference times the CPU oracle port (the reference itself needs ROS/OpenCV/PCL and cannot be built in
-this image) with all host threads on the same workload, a bounded sample of frames per step.
+--impl reference times the CPU oracle port with all host threads on the same workload, a bounded sample per step
+(same sample rule as cpu_baseline).  The reference's own glue is compiled from its sources in oracle/_ref, but its
+arithmetic lives in OpenCV / PCL, which this image does not have: the timed code is the cv2-pinned C port.
 """
 from __future__ import annotations
 
@@ -36,12 +47,59 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, BORDER = 3840, 2160, 40
-FRAMES_PER_STEP = 1024
-RING = 16                 # device-resident frame slots: 16 x (33.2 MB in + 125.1 MB out) = 2.5 GB >> 126 MB L2
-N_PTS = (W - 2 * BORDER) * (H - 2 * BORDER)
-ALG_BYTES_PER_FRAME = 20 * N_PTS   # 4 B disparity read + 16 B point written per kept pixel
-METRIC = "Mpixels/s disparity->PointCloud2 (3840x2160 float32 disparity: reproject + 40px crop + XYZ1 pack)"
+BORDER = 40
+METRIC = "Mpixels/s disparity->PointCloud2"
+
+# name, frame size, entry, frames (frame sets) per step per GPU, device-resident ring, workload string (shared by
+# both arms, byte for byte), what one unit of work is
+CONFIGS = {
+    2: dict(w=752, h=480, entry="mono8", per_step=1000, ring=250,
+            workload="752x480 mono8 disparity stream (S2 scene): whole DisparityCb = median 11 + x1/8 + reproject + "
+                     "40px crop + XYZ1 pack (BASELINE configs[1])",
+            kernel="median_hist_kernel<11> + reproject_crop_kernel<u8>"),
+    3: dict(w=1280, h=720, entry="f32", per_step=64, ring=64,
+            workload="1280x720 float32 disparity (S3), batch of 64 frames: reproject + 40px crop + XYZ1 pack "
+                     "(BASELINE configs[2])",
+            kernel="reproject_crop_kernel<float,vec16,exact-rectified>"),
+    4: dict(w=3840, h=2160, entry="f32", per_step=1024, ring=16,
+            workload="3840x2160 float32 disparity (S3): reproject + 40px crop + XYZ1 pack (BASELINE configs[3])",
+            kernel="reproject_crop_kernel<float,vec16,exact-rectified>"),
+    5: dict(w=1280, h=720, entry="fusion", per_step=256, ring=64,
+            workload="depth_map_fusion: four 1280x720 mono8 maps per frame set -> score preprocessing x2, merge, "
+                     "median 3, trim -> DisparityCb on the fused 665x665 map (BASELINE configs[4])",
+            kernel="score_tile_kernel x2 + fuse_merge_kernel + median3_net_kernel + median_hist_kernel<11> + "
+                   "reproject_crop_kernel<u8>"),
+}
+OFFSETS = (-7, 15)  # launch/depth_map_fusion.launch
+
+
+def n_points(w, h):
+    return max(0, w - 2 * BORDER) * max(0, h - 2 * BORDER)
+
+
+def fusion_dims(w, h):
+    """(n, fused_w, fused_h) of the reference geometry at the launch offsets."""
+    import oracle
+    _, r1 = oracle.crop_to_square(w, h, OFFSETS[0], OFFSETS[1], OFFSETS[1])
+    _, rc = oracle.crop_to_square(w, h, 0, 0, OFFSETS[1])
+    return r1[2], rc[2] - 40, rc[2] - 40
+
+
+def unit_pixels(cfg):
+    """Input pixels of one unit of work (a frame; for config 5 the four maps of a frame set)."""
+    return cfg["w"] * cfg["h"] * (4 if cfg["entry"] == "fusion" else 1)
+
+
+def algorithmic_bytes(cfg, dims=None):
+    """SURVEY.md 8(d), per unit of work."""
+    w, h = cfg["w"], cfg["h"]
+    if cfg["entry"] == "f32":
+        return 20 * n_points(w, h)                                   # 4 B read + 16 B written per kept pixel
+    if cfg["entry"] == "mono8":
+        return (w - 70) * (h - 70) + 16 * n_points(w, h)
+    n, fw, fh = dims
+    nc = fw + 40
+    return (2 * 2 * n * n) + 6 * n * n + (nc * nc + fw * fh) + ((fw - 70) * (fh - 70) + 16 * n_points(fw, fh))
 
 
 def measured_peak():
@@ -122,7 +180,7 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -150,90 +208,188 @@ def max_over_ranks(x, world):
     return sharding.max_over_ranks(x, device="cuda") if world > 1 else x
 
 
-def cpu_port_run(n_frames, threads, repeat=1):
-    """Times the oracle port of cpp:63-85 on n_frames 4K S3 frames; returns (Mpix/s, seconds)."""
-    import oracle
-    from disparity_to_point_cloud_b200 import synth
-    q = oracle.q_from_intrinsics()
-    frames = np.empty((n_frames, H, W), dtype=np.float32)
-    base = synth.s3_float(H, W, 0)
-    for i in range(n_frames):
-        frames[i] = np.roll(base, 97 * i, axis=1)
-    cloud = np.empty((n_frames, N_PTS * 16), dtype=np.uint8)
-    cloud[:] = 0  # touch the pages: the reference's publisher would reuse a warm allocator too
-    best = None
-    for _ in range(repeat):
+def sum_over_ranks(x, world):
+    from disparity_to_point_cloud_b200 import sharding
+    return sharding.sum_over_ranks(x, device="cuda") if world > 1 else x
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: one sample rule for cpu_baseline (product arm) and for --impl reference
+# ---------------------------------------------------------------------------------------------------------
+class CpuSample:
+    """A bounded sample of the config's workload for the CPU oracle port: `threads` units (frames / frame sets)
+    processed unit-parallel on `threads` threads, PASSES times over; one call of step() is one bench step."""
+    PASSES = 4
+
+    def __init__(self, cfg, threads):
+        import oracle
+        from disparity_to_point_cloud_b200 import synth
+        self.cfg, self.threads, self.oracle = cfg, threads, oracle
+        self.q = oracle.q_from_intrinsics()
+        w, h = cfg["w"], cfg["h"]
+        self.units = threads * self.PASSES
+        if cfg["entry"] == "fusion":
+            from concurrent.futures import ThreadPoolExecutor
+            rng = np.random.default_rng(5)
+            self.sets = [[synth.s2_scene(h, w, 200 + 4 * i), synth.s2_scene(h, w, 201 + 4 * i),
+                          rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (h, w), dtype=np.uint8)]
+                         for i in range(min(threads, 8))]
+            self.pool = ThreadPoolExecutor(threads)
+            self.desc = (f"{self.PASSES} passes over {threads} frame sets (4 x {w}x{h} mono8: score preprocessing x2, "
+                         f"merge, median 3, DisparityCb), set-parallel on {threads} threads")
+            return
+        if cfg["entry"] == "f32":
+            base = synth.s3_float(h, w, 0)
+            self.frames = np.stack([np.roll(base, 97 * i, axis=1) for i in range(threads)])
+        else:
+            self.frames = np.stack([synth.s2_scene(h, w, i % 8) for i in range(threads)])
+        self.cloud = np.zeros((threads, n_points(w, h) * 16), dtype=np.uint8)  # touched: a publisher reuses warm memory
+        kind = "f32 (S3)" if cfg["entry"] == "f32" else "mono8 (S2)"
+        self.desc = f"{self.PASSES} passes over {threads} frames of {w}x{h} {kind}, frame-parallel on {threads} threads"
+
+    def _one_set(self, s):
+        o = self.oracle
+        d1, d2, s1, s2 = s
+        h, w = d1.shape
+        _, r1 = o.crop_to_square(w, h, OFFSETS[0], OFFSETS[1], OFFSETS[1])
+        _, r2 = o.crop_to_square(h, w, -OFFSETS[0], -OFFSETS[1], OFFSETS[1])
+        p1 = o.score_preprocess(s1, r1, False)                      # MatchingScoreCb1
+        p2 = o.score_preprocess(o.rotate_cw(s2), r2, True)          # MatchingScoreCb2
+        c1 = np.zeros((h, w), np.uint8)
+        c1[r1[1]:r1[1] + r1[2], r1[0]:r1[0] + r1[2]] = p1
+        rot = np.zeros((w, h), np.uint8)
+        rot[r2[1]:r2[1] + r2[2], r2[0]:r2[0] + r2[2]] = p2
+        fused, _ = o.fuse(d1, d2, c1, np.ascontiguousarray(np.rot90(rot, 1)), *OFFSETS)  # DisparityCb1/2 + merge
+        return o.disparity_cb_mono8(fused, self.q).size             # DisparityCb on the fused map
+
+    def step(self):
+        """-> seconds for self.units units"""
         t0 = time.perf_counter()
-        oracle.run_frames(frames, q, False, threads, cloud)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_frames * W * H / best / 1e6, best
+        if self.cfg["entry"] == "fusion":
+            work = [self.sets[i % len(self.sets)] for i in range(self.units)]
+            list(self.pool.map(self._one_set, work))
+        else:
+            for _ in range(self.PASSES):
+                self.oracle.run_frames(self.frames, self.q, self.cfg["entry"] == "mono8", self.threads, self.cloud)
+        return time.perf_counter() - t0
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    cfg = CONFIGS[args.config]
     threads = os.cpu_count() or 1
-    n_frames = max(threads, 8) if threads <= 32 else threads
+    sample = CpuSample(cfg, threads)
     times = []
     for i in range(args.warmup + args.steps):
-        mpix, dt = cpu_port_run(n_frames, threads)
+        dt = sample.step()
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    value = n_frames * W * H / (ms / 1e3) / 1e6
-    sample = f"{n_frames} frames of 3840x2160 f32 (S3) per step, frame-parallel on {threads} threads"
+    value = sample.units * unit_pixels(cfg) / (ms / 1e3) / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3840x2160 float32 disparity frames, reproject+crop+pack (BASELINE configs[3])",
-                   "note": "reference node needs ROS1+OpenCV+PCL (unbuildable here): this is the CPU oracle port of "
-                           "src/disparity_to_point_cloud.cpp:63-85, pinned bit-exact against cv2"},
-        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": cfg["workload"], "units_per_step": sample.units,
+                   "note": "the reference's arithmetic lives in OpenCV / PCL (not installed here): the timed code is the "
+                           "CPU oracle port, pinned bit-exact against cv2 and against the reference's own compiled "
+                           "glue (oracle/_ref)"},
+        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": threads, "kind": "port",
+                         "sample": sample.desc + " per step"},
         "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# product arm
+# ---------------------------------------------------------------------------------------------------------
+def pcie_ceiling(torch, world, h2d_bytes, d2h_bytes, seconds=0.5):
+    """Raw pinned cudaMemcpyAsync traffic of the e2e path's shape -- h2d_bytes in and d2h_bytes out per unit, two
+    streams, nothing else -- on every rank at once.  -> (GB/s summed over ranks and directions, units/s)."""
+    from disparity_to_point_cloud_b200 import pcie
+    return pcie.measure(torch, world, h2d_bytes, d2h_bytes, seconds, barrier_sync, max_over_ranks, sum_over_ranks)
+
+
 def run_ours(args):
     import torch
 
     import disparity_to_point_cloud_b200 as d2pc
-    from disparity_to_point_cloud_b200 import synth
+    from disparity_to_point_cloud_b200 import sharding, synth
 
-    rank, world, local = dist_setup(args.gpus)
+    cfg = CONFIGS[args.config]
+    w, h, entry = cfg["w"], cfg["h"], cfg["entry"]
+    rank, world, local = dist_setup()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
-    from disparity_to_point_cloud_b200 import sharding
-    # frames are independent: weak = every rank runs args.frames frames per step, strong = args.frames are
-    # sharded i mod G (BASELINE configs[3] wording); no data-path collective either way
-    per_rank = sharding.frames_per_rank(args.frames, world, args.scaling)
-    frames_per_step = per_rank[rank]
-    total_frames_per_step = sum(per_rank)
-    ring = min(RING, max(frames_per_step, 1))
-    launches_per_step = (frames_per_step + ring - 1) // ring
+    # units are independent: weak = every rank runs per_step units per step, strong = per_step units are sharded
+    # i mod G; no data-path collective either way
+    per_step = args.frames if args.frames > 0 else cfg["per_step"]
+    per_rank = sharding.frames_per_rank(per_step, world, args.scaling)
+    units_per_step = per_rank[rank]
+    total_units_per_step = sum(per_rank)
+    ring = min(cfg["ring"], max(units_per_step, 1))
 
-    ctx = d2pc.Context(device=local, n_slots=args.slots)
+    ctx = d2pc.Context(device=local, n_slots=args.slots, offset_x=OFFSETS[0], offset_y=OFFSETS[1])
     stream = torch.cuda.ExternalStream(ctx.compute_stream(), device=torch.device("cuda", local))
+    dims = None
+    # ---- resident inputs: `ring` distinct units in HBM (seeded per rank so ranks do not share data)
+    if entry == "f32":
+        npts = n_points(w, h)
+        base = torch.from_numpy(synth.s3_float(h, w, 1000 * rank)).cuda()
+        d_in = torch.empty((ring, h, w), dtype=torch.float32, device="cuda")
+        for i in range(ring):
+            d_in[i] = torch.roll(base, shifts=131 * i + 7, dims=1)
+        out_stride = npts * 16
+        d_out = torch.empty((ring, out_stride), dtype=torch.uint8, device="cuda")
 
-    # ---- resident inputs: RING distinct S3 frames (seeded per rank so ranks do not share data)
-    base = torch.from_numpy(synth.s3_float(H, W, 1000 * rank)).cuda()
-    d_in = torch.empty((ring, H, W), dtype=torch.float32, device="cuda")
-    for i in range(ring):
-        d_in[i] = torch.roll(base, shifts=131 * i + 7, dims=1)
-    out_stride = N_PTS * 16
-    d_out = torch.empty((ring, out_stride), dtype=torch.uint8, device="cuda")
+        def launch(n):
+            ctx.reproject_f32_device(d_in.data_ptr(), n, w, h, w * 4, w * h * 4, d_out.data_ptr(), out_stride)
+    elif entry == "mono8":
+        npts = n_points(w, h)
+        eight = torch.from_numpy(np.stack([synth.s2_scene(h, w, 1000 * rank + i) for i in range(8)])).cuda()
+        d_in = eight.repeat((ring + 7) // 8, 1, 1)[:ring].contiguous()
+        out_stride = npts * 16
+        d_out = torch.empty((ring, out_stride), dtype=torch.uint8, device="cuda")
+
+        def launch(n):
+            ctx.reproject_mono8_device(d_in.data_ptr(), n, w, h, w, w * h, d_out.data_ptr(), out_stride)
+    else:
+        st, r1, r2, rc, dims = ctx.fuse_geometry(w, h)
+        n_sq, fw, fh = dims
+        npts = n_points(fw, fh)
+        rng = np.random.default_rng(1000 * rank + 5)
+        eight = np.stack([np.stack([synth.s2_scene(h, w, 1000 * rank + 2 * i), synth.s2_scene(h, w, 1000 * rank + 2 * i + 1),
+                                    rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (h, w), dtype=np.uint8)])
+                          for i in range(8)])
+        d_in = torch.from_numpy(eight).cuda().repeat((ring + 7) // 8, 1, 1, 1)[:ring].contiguous()
+        d_pre = torch.empty((2, n_sq, n_sq), dtype=torch.uint8, device="cuda")
+        d_fused = torch.empty((fh, fw), dtype=torch.uint8, device="cuda")
+        d_comb = torch.empty((n_sq, n_sq), dtype=torch.uint8, device="cuda")
+        out_stride = npts * 16
+        d_out = torch.empty((ring, out_stride), dtype=torch.uint8, device="cuda")
+        fb = w * h
+
+        def launch(n):
+            # one node pass per frame set: MatchingScoreCb1/2 -> DisparityCb1/2 + publishFusedDepthMap -> DisparityCb
+            for i in range(n):
+                p = d_in.data_ptr() + i * 4 * fb
+                ctx.preprocess_score_device(p + 2 * fb, w, h, w, 1, d_pre[0].data_ptr())
+                ctx.preprocess_score_device(p + 3 * fb, w, h, w, 2, d_pre[1].data_ptr())
+                ctx.fuse_preprocessed_device(p, p + fb, d_pre[0].data_ptr(), d_pre[1].data_ptr(), w, h, w,
+                                             d_fused.data_ptr(), d_comb.data_ptr())
+                ctx.reproject_mono8_device(d_fused.data_ptr(), 1, fw, fh, fw, fw * fh, d_out.data_ptr() + i * out_stride,
+                                           out_stride)
     torch.cuda.synchronize()
 
     def kernel_step():
-        left = frames_per_step
+        left = units_per_step
         while left > 0:
             n = min(ring, left)
-            ctx.reproject_f32_device(d_in.data_ptr(), n, W, H, W * 4, W * H * 4, d_out.data_ptr(), out_stride)
+            launch(n)
             left -= n
 
     for _ in range(args.warmup):
@@ -253,199 +409,121 @@ def run_ours(args):
     launches = ctx.launch_count() - l0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1), world)
     ms_step = ms_total / args.steps
-    value = total_frames_per_step * W * H / (ms_step / 1e3) / 1e6
+    value = total_units_per_step * unit_pixels(cfg) / (ms_step / 1e3) / 1e6
 
-    # one frame checked on the device path so a broken kernel can not post a number
-    probe = d_out[1, :64].cpu().numpy().view(np.float32)
+    # one cloud checked on the device path so a broken kernel can not post a number
+    probe = d_out[min(1, ring - 1), :64].cpu().numpy().view(np.float32)
     assert probe[3] == 1.0 and probe[7] == 1.0, "kernel output is not XYZ1 points"
 
     peak, peak_src = measured_peak()
-    per_launch_s = (ms_total / 1e3) / launches
-    achieved = ALG_BYTES_PER_FRAME * ring / per_launch_s / 1e9
+    alg = algorithmic_bytes(cfg, dims)
+    unit_s = (ms_total / 1e3) / (args.steps * units_per_step)
+    achieved = alg / unit_s / 1e9
+    api_calls = args.steps * ((units_per_step + ring - 1) // ring)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "reproject_crop_kernel<float,vec16,exact-rectified>",
-                "bytes_per_launch": ALG_BYTES_PER_FRAME * ring, "launch_us": per_launch_s * 1e6}
+                "traffic": None, "peak_source": peak_src, "kernel": cfg["kernel"],
+                "bytes_per_launch": alg * ring, "launch_us": unit_s * ring * 1e6,
+                "note": "per device-entry call of %d unit(s); achieved = algorithmic bytes / CUDA-event time" % ring}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch_ring16")
+            t = json.load(open(tr))
+            roofline["traffic"] = t.get("by_config", {}).get(str(args.config)) or (
+                t.get("dram_bytes_per_launch_ring16") if args.config == 4 else None)
         except Exception:
             pass
 
-    # ---- end to end: pinned host frames -> H2D -> kernel -> D2H, through d2pc_process_stream
-    e2e_frames = args.e2e_frames if args.e2e_frames > 0 else frames_per_step
-    e2e_total = sharding.sum_over_ranks(e2e_frames, device="cuda") if world > 1 else e2e_frames
+    # ---- end to end: pinned host frames -> H2D -> kernels -> D2H, through the C ABI's streaming entry
+    e2e_units = args.e2e_frames if args.e2e_frames > 0 else max(units_per_step, 256 if entry != "fusion" else 128)
+    e2e_total = sum_over_ranks(e2e_units, world)
     host_ring = 8
-    pin = d2pc.PinnedArray((host_ring, H, W), np.float32)
-    hb = synth.s3_float(H, W, 1000 * rank + 1)
-    for i in range(host_ring):
-        pin.array[i] = np.roll(hb, 61 * i, axis=1)
+    if entry == "fusion":
+        pin = d2pc.PinnedArray((host_ring, 4, h, w), np.uint8)
+        pin.array[:] = eight
+        in_bytes = 4 * w * h
+    elif entry == "mono8":
+        pin = d2pc.PinnedArray((host_ring, h, w), np.uint8)
+        for i in range(host_ring):
+            pin.array[i] = synth.s2_scene(h, w, 1000 * rank + 100 + i)
+        in_bytes = w * h
+    else:
+        pin = d2pc.PinnedArray((host_ring, h, w), np.float32)
+        hb = synth.s3_float(h, w, 1000 * rank + 1)
+        for i in range(host_ring):
+            pin.array[i] = np.roll(hb, 61 * i, axis=1)
+        in_bytes = 4 * w * h
+    out_bytes = npts * 16
     checks = {}
 
     def sink(idx, cloud):
         if idx == 1:
-            checks["first"] = cloud.bytes_view()[:32].copy()
             checks["width"] = cloud.width
 
     def e2e_step(n, check=False):
         # the timed call hands every cloud to a NULL sink inside the C ABI (no Python per frame);
         # the warm-up call looks at one cloud so a broken pipeline can not post a number
-        ctx.process_stream(pin.array, collect=False, sink=sink if check else None, n_frames=n)
+        if entry == "fusion":
+            ctx.process_fusion_stream(pin.array, collect=False, sink=sink if check else None, n_sets=n)
+        else:
+            ctx.process_stream(pin.array, collect=False, sink=sink if check else None, n_frames=n)
 
     e2e_step(host_ring, check=True)  # warm-up: allocates the slot buffers
     barrier_sync(world)
     t0 = time.perf_counter()
-    e2e_step(e2e_frames)
+    if args.stagger_us:
+        time.sleep(rank * args.stagger_us * 1e-6)  # experiment: ranks out of phase (the delay is inside the timed span)
+    e2e_step(e2e_units)
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-    e2e_value = e2e_total * W * H / e2e_s / 1e6
-    assert checks.get("width") == N_PTS
-    e2e = {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": frames_per_step * W * H * 4,
-           "d2h_bytes_per_step": frames_per_step * N_PTS * 16, "frames_timed": e2e_frames,
-           "frames_per_s": e2e_total / e2e_s, "timer": "wall clock between device syncs, max over ranks"}
+    e2e_value = e2e_total * unit_pixels(cfg) / e2e_s / 1e6
+    assert checks.get("width") == npts
+    e2e = {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": units_per_step * in_bytes,
+           "d2h_bytes_per_step": units_per_step * out_bytes, "frames_timed": int(e2e_total),
+           "frames_per_s": e2e_total / e2e_s, "gbs": e2e_total * (in_bytes + out_bytes) / e2e_s / 1e9,
+           "timer": "wall clock between device syncs, max over ranks; frames_timed and gbs are all-rank totals",
+           "slots": args.slots, "pinned": "thp" if os.environ.get("D2PC_PINNED_THP", "0") not in ("", "0") else "cudaHostAlloc",
+           "stagger_us": args.stagger_us}
     pin.free()
+    if not args.no_ceiling:
+        ceil_gbs, ceil_units = pcie_ceiling(torch, world, in_bytes, out_bytes)
+        e2e["ceiling_gbs"] = ceil_gbs
+        e2e["frac_of_ceiling"] = e2e["gbs"] / ceil_gbs if ceil_gbs else None
+        e2e["ceiling_note"] = ("plain pinned cudaMemcpyAsync, %d B in + %d B out per unit on two streams, all %d rank(s) "
+                               "at once, no kernels" % (in_bytes, out_bytes, world))
 
     cpu_baseline = None
-    extras = {}
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        n = 8 if threads <= 16 else min(threads, 64)
-        mpix, dt = cpu_port_run(n, threads)
-        mpix1, dt1 = cpu_port_run(2, 1)
-        cpu_baseline = {"value": mpix, "unit": "Mpixel/s", "cores": threads, "kind": "port",
-                        "sample": f"{n} frames 3840x2160 f32 (S3), frame-parallel on {threads} threads, {dt:.2f} s; "
-                                  f"single thread (as the reference node runs): {mpix1:.1f} Mpixel/s"}
-        if not args.no_extras:
-            extras = run_extras(ctx, stream, torch, d2pc, synth)
+        sample = CpuSample(cfg, threads)
+        sample.step()
+        dts = [sample.step() for _ in range(3)]
+        dt = sum(dts) / len(dts)
+        cpu_baseline = {"value": sample.units * unit_pixels(cfg) / dt / 1e6, "unit": "Mpixel/s", "cores": threads,
+                        "kind": "port", "sample": sample.desc + f"; mean of 3 timed steps of {dt:.2f} s after 1 warm-up"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3840x2160 float32 disparity (S3), %d frames per GPU per step, reproject+crop+pack "
-                                   "(BASELINE configs[3])" % frames_per_step,
-                       "frames_per_step_per_gpu": frames_per_step, "resident_ring_frames": ring,
-                       "l2_policy": "inputs+outputs of one launch are 2.5 GB (>> 126 MB L2), no flush needed",
+            "vs_baseline": None, "dtype": "f64" if entry != "fusion" else "u8+f64", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "config": args.config,
+                       "units_per_step_per_gpu": units_per_step, "resident_ring_units": ring,
+                       "l2_policy": "the ring of resident inputs+outputs is %.0f MB (> 126 MB L2), no flush needed"
+                                    % (ring * (in_bytes + out_bytes) / 1e6),
                        "arith": "EXACT (bit-identical to cv::reprojectImageTo3D)", "filter": "CROP (reference)",
-                       "frames_per_s": total_frames_per_step / (ms_step / 1e3),
-                       "sharding": "frame i -> rank i mod G, no collective on the data path"},
+                       "units_per_s": total_units_per_step / (ms_step / 1e3),
+                       "sharding": "unit i -> rank i mod G, no collective on the data path"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "extras": extras,
+            "api_calls_timed": api_calls, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+        if args.append:
+            with open(args.append, "a") as f:
+                f.write(json.dumps(line) + "\n")
     ctx.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
-
-
-def _time_launches(torch, stream, fn, iters, warm=3):
-    for _ in range(warm):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(iters):
-        fn()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters / 1e3
-
-
-def run_extras(ctx, stream, torch, d2pc, synth):
-    """Other BASELINE configs, kernel-only, short.  Reported for context; not the headline."""
-    peak, _ = measured_peak()
-    out = {}
-    # config 3: 1280x720 x 64 resident (236 MB in + 786 MB out > L2)
-    w, h, f = 1280, 720, 64
-    n = (w - 80) * (h - 80)
-    base = torch.from_numpy(synth.s3_float(h, w, 3)).cuda()
-    d_in = torch.stack([torch.roll(base, 17 * i, dims=1) for i in range(f)]).contiguous()
-    d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
-    s = _time_launches(torch, stream, lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4,
-                                                                       d_out.data_ptr(), n * 16), 20)
-    out["config3_1280x720x64_kernel"] = {"Mpixel/s": f * w * h / s / 1e6, "frames/s": f / s,
-                                         "GB/s": 20 * n * f / s / 1e9, "frac_of_hbm_peak": 20 * n * f / s / 1e9 / peak}
-    # same batch, CROP_FINITE (decoupled look-back compaction); S3 has ~0.4% zero disparities
-    d_cnt = torch.zeros(f, dtype=torch.int32, device="cuda")
-    ctx.set_filter_mode(d2pc.FILTER_CROP_FINITE)
-    s = _time_launches(torch, stream, lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4,
-                                                                       d_out.data_ptr(), n * 16, d_cnt.data_ptr()), 20)
-    ctx.set_filter_mode(d2pc.FILTER_CROP)
-    kept = int(d_cnt.sum().item())
-    by = 4 * n * f + 16 * kept
-    out["config3_crop_finite_kernel"] = {"Mpixel/s": f * w * h / s / 1e6, "GB/s": by / s / 1e9,
-                                         "frac_of_hbm_peak": by / s / 1e9 / peak, "kept_fraction": kept / (n * f)}
-    # the literal any-Q exact path on the same batch (what a non-rectified Q would take)
-    ctx.set_tuning("force_generic", 1)
-    s = _time_launches(torch, stream, lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4,
-                                                                       d_out.data_ptr(), n * 16), 20)
-    ctx.set_tuning("force_generic", 0)
-    out["config3_generic_q_exact_kernel"] = {"Mpixel/s": f * w * h / s / 1e6, "frac_of_hbm_peak": 20 * n * f / s / 1e9 / peak}
-    # FAST arithmetic on the same batch
-    ctx.set_arith_mode(d2pc.ARITH_FAST)
-    s = _time_launches(torch, stream, lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4,
-                                                                       d_out.data_ptr(), n * 16), 20)
-    ctx.set_arith_mode(d2pc.ARITH_EXACT)
-    out["config3_fast_arith_kernel"] = {"Mpixel/s": f * w * h / s / 1e6, "frac_of_hbm_peak": 20 * n * f / s / 1e9 / peak}
-    del d_in, d_out
-    # mono8 entry (median 11 + reproject), 752x480 x 256 resident
-    w, h, f = 752, 480, 256
-    n = (w - 80) * (h - 80)
-    d_img = torch.from_numpy(np.stack([synth.s2_scene(h, w, i) for i in range(8)])).cuda().repeat(f // 8, 1, 1)
-    d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
-    s = _time_launches(torch, stream, lambda: ctx.reproject_mono8_device(d_img.data_ptr(), f, w, h, w, w * h,
-                                                                         d_out.data_ptr(), n * 16), 10)
-    by = ((w - 70) * (h - 70) + 16 * n) * f
-    out["config2_752x480_mono8x256_kernel"] = {"Mpixel/s": f * w * h / s / 1e6, "frames/s": f / s,
-                                               "frac_of_hbm_peak": by / s / 1e9 / peak}
-    # config 2 end to end: 752x480 mono8 stream, 1000 frames, pinned, 3 slots
-    pin = d2pc.PinnedArray((8, h, w), np.uint8)
-    for i in range(8):
-        pin.array[i] = synth.s2_scene(h, w, 100 + i)
-    ctx.process_stream(pin.array, collect=False)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    ctx.process_stream(pin.array, collect=False, n_frames=1000)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    out["config2_752x480_mono8_stream_e2e"] = {"frames/s": 1000 / dt, "Mpixel/s": 1000 * w * h / dt / 1e6}
-    pin.free()
-    # config 5: four 1280x720 maps -> score preprocessing -> fuse -> median 3 -> trim -> DisparityCb (665x665)
-    w, h = 1280, 720
-    fctx = d2pc.Context(device=torch.cuda.current_device(), offset_x=-7, offset_y=15)
-    fstream = torch.cuda.ExternalStream(fctx.compute_stream())
-    four = [torch.from_numpy(synth.s2_scene(h, w, 200 + i)).cuda() for i in range(4)]
-    st, r1, r2, rc, dims = fctx.fuse_geometry(w, h)
-    n_sq, fw, fh = dims
-    d_fused = torch.empty((fh, fw), dtype=torch.uint8, device="cuda")
-    d_comb = torch.empty((n_sq, n_sq), dtype=torch.uint8, device="cuda")
-    d_pre = [torch.empty((n_sq, n_sq), dtype=torch.uint8, device="cuda") for _ in range(2)]
-    npts = (fw - 80) * (fh - 80)
-    d_cloud = torch.empty(npts * 16, dtype=torch.uint8, device="cuda")
-    torch.cuda.synchronize()
-    s = _time_launches(torch, fstream, lambda: fctx.fuse_device(four[0].data_ptr(), four[1].data_ptr(),
-                                                                four[2].data_ptr(), four[3].data_ptr(), w, h, w,
-                                                                d_fused.data_ptr(), d_comb.data_ptr()), 50)
-    out["config5_fuse_merge_median3_kernels"] = {"us": s * 1e6, "Mpixel/s (merged)": n_sq * n_sq / s / 1e6,
-                                                 "GB/s (6 n^2)": 6 * n_sq * n_sq / s / 1e9}
-    s = _time_launches(torch, fstream, lambda: [fctx.preprocess_score_device(four[2 + i].data_ptr(), w, h, w, i + 1,
-                                                                             d_pre[i].data_ptr()) for i in range(2)], 50)
-    out["config5_score_preprocess_x2_kernels"] = {"us": s * 1e6}
-    s = _time_launches(torch, fstream, lambda: fctx.reproject_mono8_device(d_fused.data_ptr(), 1, fw, fh, fw, fw * fh,
-                                                                           d_cloud.data_ptr(), npts * 16), 50)
-    out["config5_fused_665x665_callback_kernels"] = {"us": s * 1e6, "points": npts}
-    hfour = [synth.s2_scene(h, w, 200 + i) for i in range(4)]
-    fctx.fuse_then_process(*hfour)
-    t0 = time.perf_counter()
-    for _ in range(50):
-        fctx.fuse_then_process(*hfour)
-    dt = (time.perf_counter() - t0) / 50
-    out["config5_fuse_then_process_host_e2e"] = {"ms": dt * 1e3, "frame_sets/s": 1 / dt,
-                                                 "note": "4 pageable 1280x720 frames in, 342225-point cloud out, synchronous"}
-    fctx.close()
-    return out
 
 
 def main():
@@ -454,12 +532,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP, help="frames per GPU per step")
-    ap.add_argument("--e2e-frames", type=int, default=0, help="frames timed end to end (0 = one full step)")
-    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS), help="BASELINE workload (SURVEY 8 numbering)")
+    ap.add_argument("--frames", type=int, default=0, help="units per GPU per step (0 = the config's own)")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="units timed end to end (0 = one full step, >= 256)")
     ap.add_argument("--slots", type=int, default=3, help="pipeline slots per GPU of the end-to-end path")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: --frames per GPU per step; strong: --frames in total, sharded i mod G")
+                    help="weak: per-step units per GPU; strong: per-step units in total, sharded i mod G")
+    ap.add_argument("--stagger-us", type=int, default=0, help="experiment: rank r starts its end-to-end stream r x this late")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ceiling", action="store_true", help="skip the raw-copy ceiling of the e2e path")
+    ap.add_argument("--append", default="", help="also append the JSON line to this file (profiles/configs_r2.json)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -124,8 +124,14 @@ SYMBOLS = [
     ("d2pc_colorize_depth", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Image)]),
     ("d2pc_fuse_device", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                    C.c_size_t, C.c_void_p, C.c_void_p]),
+    ("d2pc_fuse_preprocessed_device", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p]),
     ("d2pc_fuse_then_process", C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint32, C.c_uint32, C.POINTER(Cloud)]),
+    ("d2pc_submit_fusion", C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                     C.c_uint32, C.c_uint32, C.c_int]),
+    ("d2pc_process_fusion_stream", C.c_int, [_ctx, C.c_void_p, C.c_uint64, C.c_size_t, C.c_uint64, C.c_uint32,
+                                             C.c_uint32, C.c_uint32, C.c_int, CLOUD_SINK, C.c_void_p]),
     ("d2pc_serialize_pointcloud2", C.c_size_t, [_ctx, C.POINTER(Cloud), C.c_uint32, C.c_uint32, C.c_uint32,
                                                 C.c_void_p, C.c_size_t]),
     ("d2pc_set_tuning", C.c_int, [_ctx, C.c_char_p, C.c_int]),
@@ -444,6 +450,10 @@ class Context:
         self._check(lib().d2pc_fuse_device(self._h, d_d1, d_d2, d_s1, d_s2, w, h, step, d_fused, d_combined or None),
                     "d2pc_fuse_device")
 
+    def fuse_preprocessed_device(self, d_d1, d_d2, d_s1c, d_s2c, w, h, step, d_fused, d_combined=0):
+        self._check(lib().d2pc_fuse_preprocessed_device(self._h, d_d1, d_d2, d_s1c, d_s2c, w, h, step, d_fused,
+                                                        d_combined or None), "d2pc_fuse_preprocessed_device")
+
     def fuse_then_process(self, d1, d2, s1, s2) -> np.ndarray:
         arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (d1, d2, s1, s2)]
         self._same_shape(arrs, "fuse_then_process")
@@ -453,6 +463,36 @@ class Context:
                     "d2pc_fuse_then_process")
         self.last_cloud = cl
         return cl.bytes_view().copy()
+
+    def submit_fusion(self, slot: int, d1, d2, s1, s2, preprocess_scores: bool = True):
+        """One whole fusion-node pass + DisparityCb on pipeline slot `slot` (collect with wait(slot))."""
+        arrs = [np.asarray(a) for a in (d1, d2, s1, s2)]
+        self._same_shape(arrs, "submit_fusion")
+        assert all(a.dtype == np.uint8 and a.strides[1] == 1 and a.strides[0] == arrs[0].strides[0] for a in arrs)
+        h, w = arrs[0].shape
+        self._keep[slot] = (arrs, None)
+        self._check(lib().d2pc_submit_fusion(self._h, slot, *(a.ctypes.data for a in arrs), w, h, arrs[0].strides[0],
+                                             1 if preprocess_scores else 0), "d2pc_submit_fusion")
+
+    def process_fusion_stream(self, sets: np.ndarray, preprocess_scores: bool = True, collect: bool = True, sink=None,
+                              n_sets: int | None = None):
+        """sets: (S, 4, H, W) uint8, the four frames of a set in the order d1, d2, s1, s2; n_sets > S cycles."""
+        assert sets.ndim == 4 and sets.shape[1] == 4 and sets.dtype == np.uint8 and sets.strides[3] == 1
+        assert sets.strides[1] == sets.strides[2] * sets.shape[2]
+        out = []
+
+        def _sink(user, idx, cloud):
+            if sink is not None:
+                sink(idx, cloud.contents)
+            if collect:
+                out.append(cloud.contents.bytes_view().copy())
+
+        cb = CLOUD_SINK(_sink) if (collect or sink is not None) else C.cast(None, CLOUD_SINK)
+        sn, _, h, w = sets.shape
+        rc = lib().d2pc_process_fusion_stream(self._h, sets.ctypes.data, n_sets or sn, sets.strides[0], sn, w, h,
+                                              sets.strides[2], 1 if preprocess_scores else 0, cb, None)
+        self._check(rc, "d2pc_process_fusion_stream")
+        return out
 
     def serialize_pointcloud2(self, cloud: Cloud, seq=0, sec=0, nsec=0) -> bytes:
         need = lib().d2pc_serialize_pointcloud2(self._h, C.byref(cloud), seq, sec, nsec, None, 0)

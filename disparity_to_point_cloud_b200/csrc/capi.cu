@@ -17,10 +17,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <utility>
 #include <vector>
+
+#include <sys/mman.h>
 
 #include "fusion.h"
 #include "median.h"
@@ -46,6 +49,8 @@ struct PinBuf {
 struct Slot {
   PinBuf h_in, h_out;
   DevBuf d_in, d_med, d_out, d_scratch, d_tables, d_cells;
+  // fusion pipeline (d2pc_submit_fusion): the four input frames, the two preprocessed scores, merge outputs
+  DevBuf d_fuse_in[4], d_pre[2], d_container, d_combined, d_fused;
   uint32_t *d_count = nullptr;  // [0] = kept points, [1] = compaction ticket
   uint32_t *h_count = nullptr;  // pinned
   cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr;
@@ -128,13 +133,68 @@ int grow_dev(d2pc_ctx *ctx, DevBuf &b, size_t bytes, bool zero = false) {
   b.cap = cap;
   return D2PC_OK;
 }
+// Page-locked host memory.  Default: cudaHostAlloc.  With D2PC_PINNED_THP=1 in the environment: an anonymous
+// 2 MB-aligned mapping advised MADV_HUGEPAGE, touched, then cudaHostRegister'ed -- 512x fewer pages for the IOMMU
+// and the DMA engines to walk (an experiment for the multi-GPU end-to-end path).
+struct HostBlock {
+  void *p;
+  size_t bytes;
+};
+std::mutex g_thp_mutex;
+std::vector<HostBlock> g_thp_blocks;
+
+cudaError_t pinned_alloc(void **out, size_t bytes) {
+  static const bool thp = [] {
+    const char *v = getenv("D2PC_PINNED_THP");
+    return v && atoi(v) != 0;
+  }();
+  if (!thp) return cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+  const size_t huge = (size_t)2 << 20, len = align_up(bytes, huge);
+  void *p = mmap(nullptr, len + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) return cudaErrorMemoryAllocation;
+  uint8_t *a = reinterpret_cast<uint8_t *>(align_up(reinterpret_cast<uintptr_t>(p), huge));
+  // give back the unaligned head and tail so that munmap(a, len) releases everything
+  if (a != p) munmap(p, (size_t)(a - static_cast<uint8_t *>(p)));
+  const size_t tail = (static_cast<uint8_t *>(p) + len + huge) - (a + len);
+  if (tail) munmap(a + len, tail);
+  madvise(a, len, MADV_HUGEPAGE);
+  for (size_t i = 0; i < len; i += 4096) a[i] = 0;  // fault the pages in (as huge pages where the kernel can)
+  cudaError_t e = cudaHostRegister(a, len, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    munmap(a, len);
+    return e;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_thp_mutex);
+    g_thp_blocks.push_back({a, len});
+  }
+  *out = a;
+  return cudaSuccess;
+}
+cudaError_t pinned_free(void *p) {
+  {
+    std::lock_guard<std::mutex> lk(g_thp_mutex);
+    for (size_t i = 0; i < g_thp_blocks.size(); ++i)
+      if (g_thp_blocks[i].p == p) {
+        const size_t len = g_thp_blocks[i].bytes;
+        g_thp_blocks.erase(g_thp_blocks.begin() + (long)i);
+        cudaError_t e = cudaHostUnregister(p);
+        munmap(p, len);
+        return e;
+      }
+  }
+  return cudaFreeHost(p);
+}
+
 int grow_pin(d2pc_ctx *ctx, PinBuf &b, size_t bytes) {
   if (bytes <= b.cap) return D2PC_OK;
-  if (b.p) CU(ctx, cudaFreeHost(b.p));
+  if (b.p) CU(ctx, pinned_free(b.p));
   b.p = nullptr;
   b.cap = 0;
   const size_t cap = align_up(bytes, 1 << 16);
-  CU(ctx, cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
+  void *p = nullptr;
+  CU(ctx, pinned_alloc(&p, cap));
+  b.p = static_cast<uint8_t *>(p);
   b.cap = cap;
   return D2PC_OK;
 }
@@ -143,7 +203,7 @@ void free_dev(DevBuf &b) {
   b = DevBuf{};
 }
 void free_pin(PinBuf &b) {
-  if (b.p) cudaFreeHost(b.p);
+  if (b.p) pinned_free(b.p);
   b = PinBuf{};
 }
 
@@ -531,6 +591,8 @@ void d2pc_destroy(d2pc_ctx *ctx) {
     free_pin(s.h_in), free_pin(s.h_out);
     free_dev(s.d_in), free_dev(s.d_med), free_dev(s.d_out), free_dev(s.d_scratch), free_dev(s.d_tables);
     free_dev(s.d_cells);
+    for (auto &b : s.d_fuse_in) free_dev(b);
+    free_dev(s.d_pre[0]), free_dev(s.d_pre[1]), free_dev(s.d_container), free_dev(s.d_combined), free_dev(s.d_fused);
     if (s.d_count) cudaFree(s.d_count);
     if (s.h_count) cudaFreeHost(s.h_count);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
@@ -682,7 +744,7 @@ int d2pc_process_f32(d2pc_ctx *ctx, const float *disp, uint32_t w, uint32_t h, u
 int d2pc_host_alloc(void **ptr, size_t bytes) {
   if (!ptr) return D2PC_ERR_INVALID_ARG;
   *ptr = nullptr;
-  cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  cudaError_t e = pinned_alloc(ptr, bytes ? bytes : 1);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return e == cudaErrorMemoryAllocation ? D2PC_ERR_NOMEM : D2PC_ERR_CUDA;
@@ -692,7 +754,7 @@ int d2pc_host_alloc(void **ptr, size_t bytes) {
 int d2pc_host_free(void *ptr) {
   if (!ptr) return D2PC_OK;
   g_host_gen.fetch_add(1, std::memory_order_acq_rel);  // contexts forget what they knew about this address
-  return cudaFreeHost(ptr) == cudaSuccess ? D2PC_OK : D2PC_ERR_CUDA;
+  return pinned_free(ptr) == cudaSuccess ? D2PC_OK : D2PC_ERR_CUDA;
 }
 int d2pc_host_register(void *ptr, size_t bytes) {
   if (!ptr || !bytes) return D2PC_ERR_INVALID_ARG;
@@ -846,16 +908,17 @@ int d2pc_fuse_geometry(const d2pc_ctx *ctx, uint32_t w, uint32_t h, int rect1[4]
 
 static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1, const uint8_t *s2,
                             uint32_t w, uint32_t h, size_t step, uint8_t *d_fused, uint8_t *d_combined,
-                            FuseGeometry *g_out, bool scores_cropped = false) {
+                            FuseGeometry *g_out, bool scores_cropped = false, DevBuf *container = nullptr) {
   const d2pc_config &c = ctx->cfg;
   FuseGeometry g;
   if (!fuse_geometry((int)w, (int)h, c.offset_x, c.offset_y, c.fuse_crop_left, c.fuse_crop_right, c.fuse_crop_top,
                      c.fuse_crop_bottom, &g))
     return D2PC_ERR_GEOMETRY;
   int rc;
-  if ((size_t)g.nc * g.nc > ctx->d_container.cap) {
+  DevBuf &cont = container ? *container : ctx->d_container;
+  if ((size_t)g.nc * g.nc > cont.cap) {
     CU(ctx, cudaStreamSynchronize(ctx->s_compute));
-    if ((rc = grow_dev(ctx, ctx->d_container, (size_t)g.nc * g.nc))) return rc;
+    if ((rc = grow_dev(ctx, cont, (size_t)g.nc * g.nc))) return rc;
   }
   FuseLaunch L;
   L.d1 = d1, L.d2 = d2, L.s1 = s1, L.s2 = s2;
@@ -864,7 +927,7 @@ static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2,
   L.g = g;
   L.rule = c.fuse_rule;
   L.scores_cropped = scores_cropped;
-  L.container = ctx->d_container.p;
+  L.container = cont.p;
   L.combined = d_combined;
   int nl = 0;
   CU(ctx, launch_fuse_merge(L, ctx->s_compute, &nl));
@@ -873,7 +936,7 @@ static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2,
     // :124 medianBlur on the container ROI (its edge is the replicate border), then :130 cropMat -- produced as
     // one kernel that only evaluates the pixels that survive the trim.
     MedianLaunch M;
-    M.src = ctx->d_container.p;
+    M.src = cont.p;
     M.src_step = (size_t)g.nc;
     M.width = g.nc, M.height = g.nc;
     M.ox0 = g.out_x, M.oy0 = g.out_y, M.ow = g.out_w, M.oh = g.out_h;
@@ -886,7 +949,7 @@ static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2,
     CU(ctx, launch_median_u8(M, ctx->s_compute, &nl));
     ctx->launches += nl;
   } else {
-    CU(ctx, cudaMemcpy2DAsync(d_fused, g.out_w, ctx->d_container.p + (size_t)g.out_y * g.nc + g.out_x, g.nc, g.out_w,
+    CU(ctx, cudaMemcpy2DAsync(d_fused, g.out_w, cont.p + (size_t)g.out_y * g.nc + g.out_x, g.nc, g.out_w,
                               g.out_h, cudaMemcpyDeviceToDevice, ctx->s_compute));
   }
   if (g_out) *g_out = g;
@@ -900,6 +963,15 @@ int d2pc_fuse_device(d2pc_ctx *ctx, const uint8_t *d_d1, const uint8_t *d_d2, co
   if (w == 0 || h == 0 || step < w) return D2PC_ERR_BAD_DIMS;
   CU(ctx, cudaSetDevice(ctx->device));
   return fuse_device_impl(ctx, d_d1, d_d2, d_s1, d_s2, w, h, step, d_fused, d_combined, nullptr);
+}
+
+int d2pc_fuse_preprocessed_device(d2pc_ctx *ctx, const uint8_t *d_d1, const uint8_t *d_d2, const uint8_t *d_s1c,
+                                  const uint8_t *d_s2c, uint32_t w, uint32_t h, size_t step, uint8_t *d_fused,
+                                  uint8_t *d_combined) {
+  if (!ctx || !d_d1 || !d_d2 || !d_s1c || !d_s2c || !d_fused) return D2PC_ERR_INVALID_ARG;
+  if (w == 0 || h == 0 || step < w) return D2PC_ERR_BAD_DIMS;
+  CU(ctx, cudaSetDevice(ctx->device));
+  return fuse_device_impl(ctx, d_d1, d_d2, d_s1c, d_s2c, w, h, step, d_fused, d_combined, nullptr, /*scores_cropped=*/true);
 }
 
 static int fuse_upload_and_run(d2pc_ctx *ctx, const uint8_t *const in[4], uint32_t w, uint32_t h, uint32_t step,
@@ -1103,6 +1175,107 @@ int d2pc_fuse_then_process(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, 
   CU(ctx, cudaStreamSynchronize(ctx->s_compute));
   if (ctx->cfg.verbose) printf("Cloud size: %llu\n", (unsigned long long)kept);
   fill_cloud(ctx, s.h_out.p, kept, compact, out);
+  return D2PC_OK;
+}
+
+// ---- the whole fusion node + DisparityCb per frame set, on the slot pipeline ------------------------------------
+int d2pc_submit_fusion(d2pc_ctx *ctx, int slot, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
+                       const uint8_t *s2, uint32_t w, uint32_t h, uint32_t step, int preprocess_scores) {
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !d1 || !d2 || !s1 || !s2) return D2PC_ERR_INVALID_ARG;
+  if (w == 0 || h == 0 || w > (1u << 16) || h > (1u << 16) || step < w) return D2PC_ERR_BAD_DIMS;
+  const d2pc_config &c = ctx->cfg;
+  FuseGeometry g;
+  if (!fuse_geometry((int)w, (int)h, c.offset_x, c.offset_y, c.fuse_crop_left, c.fuse_crop_right, c.fuse_crop_top,
+                     c.fuse_crop_bottom, &g))
+    return D2PC_ERR_GEOMETRY;
+  CU(ctx, cudaSetDevice(ctx->device));
+  Slot &s = ctx->slots[slot];
+  int rc = slot_wait_idle(ctx, s);
+  if (rc) return rc;
+  const size_t pitch = align_up(w, kAlign), frame_bytes = (size_t)w * h, nn = (size_t)g.n * g.n;
+  const uint32_t fw = (uint32_t)g.out_w, fh = (uint32_t)g.out_h;
+  const uint64_t n = crop_points(fw, fh, c.border);
+  const bool compact = c.filter_mode == D2PC_FILTER_CROP_FINITE;
+  for (int i = 0; i < 4; ++i)
+    if ((rc = grow_dev(ctx, s.d_fuse_in[i], pitch * h))) return rc;
+  if ((rc = grow_dev(ctx, s.d_pre[0], nn)) || (rc = grow_dev(ctx, s.d_pre[1], nn)) ||
+      (rc = grow_dev(ctx, s.d_container, (size_t)g.nc * g.nc)) || (rc = grow_dev(ctx, s.d_combined, nn)) ||
+      (rc = grow_dev(ctx, s.d_fused, (size_t)fw * fh)) || (rc = grow_dev(ctx, s.d_med, (size_t)fw * fh)) ||
+      (rc = grow_dev(ctx, s.d_out, n * 16 + 16)) || (rc = grow_pin(ctx, s.h_out, n * 16 + 16)))
+    return rc;
+  if (compact && ((rc = grow_dev(ctx, s.d_scratch, reproject_scratch_bytes(1, fw, fh, c.border), true)) ||
+                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(fw, fh))) ||
+                  (rc = grow_dev(ctx, s.d_cells, reproject_cells_bytes(1, fw, fh, c.border)))))
+    return rc;
+
+  // ---- H2D (stream 1): pinned caller frames are DMA'd in place, pageable ones are staged
+  const uint8_t *in[4] = {d1, d2, s1, s2};
+  for (int i = 0; i < 4; ++i) {
+    const uint8_t *src = in[i];
+    size_t src_pitch = step;
+    if (!lookup_pinned(ctx, in[i])) {
+      if ((rc = grow_pin(ctx, s.h_in, 4 * frame_bytes))) return rc;
+      uint8_t *stage = s.h_in.p + i * frame_bytes;
+      if (step == w) memcpy(stage, in[i], frame_bytes);
+      else
+        for (uint32_t y = 0; y < h; ++y) memcpy(stage + (size_t)y * w, in[i] + (size_t)y * step, w);
+      src = stage, src_pitch = w;
+    }
+    CU(ctx, cudaMemcpy2DAsync(s.d_fuse_in[i].p, pitch, src, src_pitch, w, h, cudaMemcpyHostToDevice, ctx->s_h2d));
+  }
+  CU(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
+
+  // ---- kernels (stream 2): MatchingScoreCb1/2 -> merge -> median 3 + trim -> DisparityCb on the fused map
+  CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
+  const uint8_t *sc1 = s.d_fuse_in[2].p, *sc2 = s.d_fuse_in[3].p;
+  if (preprocess_scores) {
+    if ((rc = score_device_impl(ctx, s.d_fuse_in[2].p, w, h, pitch, 1, s.d_pre[0].p, nullptr)) ||
+        (rc = score_device_impl(ctx, s.d_fuse_in[3].p, w, h, pitch, 2, s.d_pre[1].p, nullptr)))
+      return rc;
+    sc1 = s.d_pre[0].p, sc2 = s.d_pre[1].p;
+  }
+  if ((rc = fuse_device_impl(ctx, s.d_fuse_in[0].p, s.d_fuse_in[1].p, sc1, sc2, w, h, pitch, s.d_fused.p, s.d_combined.p,
+                             nullptr, preprocess_scores != 0, &s.d_container)))
+    return rc;
+  rc = enqueue_kernels(ctx, s.d_fused.p, false, 1, fw, fh, fw, (size_t)fw * fh, s.d_med.p, s.d_out.p, n * 16 + 16, s.d_count,
+                       s.d_scratch.p, s.d_tables.p, s.d_cells.p, s.d_count + 1, ctx->s_compute);
+  if (rc) return rc;
+  CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
+
+  // ---- D2H (stream 3)
+  CU(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_kernel, 0));
+  if (compact) CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+  else if (n) CU(ctx, cudaMemcpyAsync(s.h_out.p, s.d_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
+  CU(ctx, cudaEventRecord(s.ev_d2h, ctx->s_d2h));
+  s.pending = true;
+  s.width = fw, s.height = fh;
+  s.n_points = n;
+  s.compact = compact;
+  s.user_dst = nullptr, s.user_cap = 0, s.user_pinned = false;
+  return D2PC_OK;
+}
+
+int d2pc_process_fusion_stream(d2pc_ctx *ctx, const uint8_t *sets, uint64_t n_sets, size_t set_stride, uint64_t ring_len,
+                               uint32_t w, uint32_t h, uint32_t step, int preprocess_scores, d2pc_cloud_sink sink,
+                               void *user) {
+  if (!ctx || (!sets && n_sets)) return D2PC_ERR_INVALID_ARG;
+  const uint64_t ns = ctx->slots.size();
+  const size_t fb = (size_t)step * h;
+  d2pc_cloud cloud;
+  uint64_t submitted = 0, retired = 0;
+  while (retired < n_sets) {
+    while (submitted < n_sets && submitted - retired < ns) {
+      const uint8_t *f = sets + (ring_len ? submitted % ring_len : submitted) * set_stride;
+      const int rc = d2pc_submit_fusion(ctx, (int)(submitted % ns), f, f + fb, f + 2 * fb, f + 3 * fb, w, h, step,
+                                        preprocess_scores);
+      if (rc) return rc;
+      ++submitted;
+    }
+    const int rc = d2pc_wait(ctx, (int)(retired % ns), &cloud);
+    if (rc) return rc;
+    if (sink) sink(user, retired, &cloud);
+    ++retired;
+  }
   return D2PC_OK;
 }
 

@@ -277,6 +277,12 @@ int d2pc_fuse_device(d2pc_ctx *ctx, const uint8_t *d_d1, const uint8_t *d_d2, co
                      const uint8_t *d_s2, uint32_t width, uint32_t height, size_t step, uint8_t *d_fused,
                      uint8_t *d_combined);
 
+/* d2pc_fuse_device with the two scores given as the n x n preprocessed caches (d2pc_preprocess_score_device
+ * output, dense): the device-resident form of d2pc_fuse_preprocessed. */
+int d2pc_fuse_preprocessed_device(d2pc_ctx *ctx, const uint8_t *d_d1, const uint8_t *d_d2, const uint8_t *d_s1_cropped,
+                                  const uint8_t *d_s2_cropped, uint32_t width, uint32_t height, size_t step,
+                                  uint8_t *d_fused, uint8_t *d_combined);
+
 /* DepthMapFusion::colorizeDepth (src/depth_map_fusion.cpp:304-358), the RAINBOW_WITH_BLACK colouring of the
  * node's debug views: mono8 in host memory -> 3 bytes per pixel in the byte order the reference stores (and labels
  * "rgb8", :298-299).  out->width = width, out->step = 3 * width. */
@@ -287,6 +293,21 @@ int d2pc_colorize_depth(d2pc_ctx *ctx, const uint8_t *gray, uint32_t width, uint
  * the fused map without leaving the device. */
 int d2pc_fuse_then_process(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
                            const uint8_t *s2, uint32_t width, uint32_t height, uint32_t step, d2pc_cloud *out);
+
+/* The same frame set on the slot pipeline (asynchronous, like d2pc_submit_mono8): H2D of the four frames,
+ * [MatchingScoreCb1/2 when preprocess_scores != 0: s1 / s2 are then the raw matching-score frames of
+ * src/depth_map_fusion.cpp:64-99; with 0 they are full frames that already hold the preprocessed scores, as for
+ * d2pc_fuse], the merge, median 3 + trim, DisparityCb on the fused map and the D2H of the cloud are enqueued on the
+ * three streams; collect the cloud with d2pc_wait(ctx, slot, &cloud).  Slots overlap frame sets. */
+int d2pc_submit_fusion(d2pc_ctx *ctx, int slot, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1,
+                       const uint8_t *s2, uint32_t width, uint32_t height, uint32_t step, int preprocess_scores);
+
+/* Streams n_sets frame sets through d2pc_submit_fusion / d2pc_wait with every slot busy; set i is read from
+ * sets + (i % ring_len) * set_stride (ring_len 0 = n_sets) as four frames of step * height bytes back to back in
+ * the order d1, d2, s1, s2.  What bench.py --config 5 times end to end. */
+int d2pc_process_fusion_stream(d2pc_ctx *ctx, const uint8_t *sets, uint64_t n_sets, size_t set_stride,
+                               uint64_t ring_len, uint32_t width, uint32_t height, uint32_t step,
+                               int preprocess_scores, d2pc_cloud_sink sink, void *user);
 
 /* ---- ROS1 wire helpers (what Publisher::publish serialises) ------------------- */
 

@@ -126,6 +126,46 @@ def test_config5_fuse_then_reproject(ctx):
     assert_same_bits(got, oracle.disparity_cb_mono8(fused, q), "config 5")
 
 
+def _node_pass_oracle(d1, d2, s1, s2, q, preprocess):
+    """MatchingScoreCb1/2 (when preprocess) -> DisparityCb1/2 -> publishFusedDepthMap -> DisparityCb, by the oracle."""
+    from oracle import nodes
+    if not preprocess:
+        fused, _ = oracle.fuse(d1, d2, s1, s2, -7, 15)
+    else:
+        o = nodes.FusionNodeOracle(-7, 15)
+        o.callback(3, s1), o.callback(4, s2), o.callback(1, d1)
+        fused = [m for m in o.callback(2, d2) if m[0] == "/fused_depth_map"][0][2]
+    return oracle.disparity_cb_mono8(np.ascontiguousarray(fused), q)
+
+
+@pytest.mark.parametrize("preprocess", [True, False])
+def test_fusion_pipeline_slots_and_stream(ctx, preprocess):
+    """d2pc_submit_fusion / d2pc_process_fusion_stream: whole node passes (the four callbacks + DisparityCb on the
+    fused map) overlapped on the slot pipeline; clouds in order, bit-identical to the oracle's node."""
+    import disparity_to_point_cloud_b200 as d2pc
+    q = golden("q_golden.npz")["q"][0]
+    h, w, n_sets = 480, 752, 5
+    pin = d2pc.PinnedArray((n_sets, 4, h, w), np.uint8)
+    rng = np.random.default_rng(77)
+    for i in range(n_sets):
+        pin.array[i, 0], pin.array[i, 1] = synth.s2_scene(h, w, 300 + i), synth.s2_scene(h, w, 400 + i)
+        pin.array[i, 2] = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        pin.array[i, 3] = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    want = [_node_pass_oracle(*pin.array[i], q, preprocess) for i in range(n_sets)]
+    clouds = ctx.process_fusion_stream(pin.array, preprocess_scores=preprocess, n_sets=2 * n_sets)
+    assert len(clouds) == 2 * n_sets
+    for i, c in enumerate(clouds):
+        assert_same_bits(c, want[i % n_sets], f"stream set {i}")
+    # explicit slots, pageable frames, waited out of order
+    a = [np.array(pin.array[0, k]) for k in range(4)]
+    b = [np.array(pin.array[3, k]) for k in range(4)]
+    ctx.submit_fusion(0, *a, preprocess_scores=preprocess)
+    ctx.submit_fusion(1, *b, preprocess_scores=preprocess)
+    assert_same_bits(ctx.wait(1), want[3], "slot 1")
+    assert_same_bits(ctx.wait(0), want[0], "slot 0")
+    pin.free()
+
+
 def test_debug_colouriser(ctx):
     """DepthMapFusion::colorizeDepth: every gray level, and a scene."""
     ramp = np.tile(np.arange(256, dtype=np.uint8), (3, 1))
