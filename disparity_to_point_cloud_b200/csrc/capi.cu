@@ -48,7 +48,7 @@ struct PinBuf {
 
 struct Slot {
   PinBuf h_in, h_out;
-  DevBuf d_in, d_med, d_out, d_scratch, d_tables, d_cells;
+  DevBuf d_in, d_med, d_out, d_scratch, d_tables;
   // fusion pipeline (d2pc_submit_fusion): the four input frames, the two preprocessed scores, merge outputs
   DevBuf d_fuse_in[4], d_pre[2], d_container, d_combined, d_fused;
   uint32_t *d_count = nullptr;  // [0] = kept points, [1] = compaction ticket
@@ -78,7 +78,7 @@ struct d2pc_ctx {
   uint64_t launches = 0;
   std::string last_cuda_error;
   // device-entry scratch
-  DevBuf d_scratch, d_tables, d_cells, d_med_batch;
+  DevBuf d_scratch, d_tables, d_med_batch;
   uint32_t *d_ticket = nullptr;
   // fusion buffers
   DevBuf d_fuse_in[4], d_container, d_combined, d_fused;
@@ -92,7 +92,7 @@ struct d2pc_ctx {
   // tuning / test hooks
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0, median_variant = 0;
   bool force_scalar = false, force_generic = false;
-  int compact_variant = 0, exact_variant = 0, pipe_stages = 0, pipe_producers = 0, pipe_consumers = 0, prefetch_dist = 0;
+  int compact_variant = 0, exact_variant = 0, prefetch_dist = 0;
   std::vector<std::pair<uintptr_t, bool>> pin_cache;  // host pointer -> pinned (cudaHostAlloc / cudaHostRegister)?
   uint64_t pin_cache_gen = 0;                         // value of g_host_gen the cache was filled under
 };
@@ -274,8 +274,7 @@ bool lookup_pinned(d2pc_ctx *ctx, const void *p) {
 // Enqueue [median] + reproject for one frame batch already on the device.
 int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_frames, uint32_t w, uint32_t h,
                     size_t step, size_t frame_stride, uint8_t *d_med, uint8_t *d_out, size_t out_stride,
-                    uint32_t *d_counts, void *scratch, void *tables, void *cells, uint32_t *ticket,
-                    cudaStream_t stream) {
+                    uint32_t *d_counts, void *scratch, void *tables, uint32_t *ticket, cudaStream_t stream) {
   const d2pc_config &c = ctx->cfg;
   const uint8_t *reproj_in = d_in;
   int nl = 0;
@@ -320,7 +319,6 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
   L.compact = c.filter_mode == D2PC_FILTER_CROP_FINITE;
   L.scratch = scratch;
   L.tables = tables;
-  L.cells = cells;
   L.ticket = ticket;
   L.epoch = L.compact ? next_epoch(ctx) : 0;
   L.sm_count = ctx->sm_count;
@@ -330,9 +328,6 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
   L.force_generic = ctx->force_generic;
   L.compact_variant = ctx->compact_variant;
   L.exact_variant = ctx->exact_variant;
-  L.pipe_stages = ctx->pipe_stages;
-  L.pipe_producers = ctx->pipe_producers;
-  L.pipe_consumers = ctx->pipe_consumers;
   L.prefetch_dist = ctx->prefetch_dist;
   CU(ctx, launch_reproject(L, stream, &nl));
   ctx->launches += nl;
@@ -378,8 +373,7 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   if ((rc = grow_dev(ctx, s.d_out, n * 16 + 16))) return rc;
   if (!user_pinned && (rc = grow_pin(ctx, s.h_out, n * 16 + 16))) return rc;
   if (compact && ((rc = grow_dev(ctx, s.d_scratch, reproject_scratch_bytes(1, w, h, ctx->cfg.border), true)) ||
-                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(w, h))) ||
-                  (rc = grow_dev(ctx, s.d_cells, reproject_cells_bytes(1, w, h, ctx->cfg.border)))))
+                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(w, h)))))
     return rc;
 
   // ---- H2D (stream 1).  Pinned caller memory is DMA'd in place; pageable memory is staged.
@@ -406,7 +400,7 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   // ---- kernels (stream 2)
   CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
   rc = enqueue_kernels(ctx, s.d_in.p, is_f32, 1, w, h, d_pitch, d_pitch * h, s.d_med.p, s.d_out.p, n * 16 + 16,
-                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_cells.p, s.d_count + 1, ctx->s_compute);
+                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
   if (rc) return rc;
   CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
 
@@ -590,7 +584,6 @@ void d2pc_destroy(d2pc_ctx *ctx) {
   for (auto &s : ctx->slots) {
     free_pin(s.h_in), free_pin(s.h_out);
     free_dev(s.d_in), free_dev(s.d_med), free_dev(s.d_out), free_dev(s.d_scratch), free_dev(s.d_tables);
-    free_dev(s.d_cells);
     for (auto &b : s.d_fuse_in) free_dev(b);
     free_dev(s.d_pre[0]), free_dev(s.d_pre[1]), free_dev(s.d_container), free_dev(s.d_combined), free_dev(s.d_fused);
     if (s.d_count) cudaFree(s.d_count);
@@ -599,7 +592,7 @@ void d2pc_destroy(d2pc_ctx *ctx) {
     if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
     if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
   }
-  free_dev(ctx->d_scratch), free_dev(ctx->d_tables), free_dev(ctx->d_cells), free_dev(ctx->d_med_batch);
+  free_dev(ctx->d_scratch), free_dev(ctx->d_tables), free_dev(ctx->d_med_batch);
   for (auto &b : ctx->d_fuse_in) free_dev(b);
   free_dev(ctx->d_container), free_dev(ctx->d_combined), free_dev(ctx->d_fused);
   free_pin(ctx->h_fused), free_pin(ctx->h_combined);
@@ -647,9 +640,6 @@ int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value) {
   else if (k == "force_generic") ctx->force_generic = value != 0;
   else if (k == "force_park" || k == "compact_variant") ctx->compact_variant = value;
   else if (k == "exact_variant") ctx->exact_variant = value;
-  else if (k == "pipe_stages") ctx->pipe_stages = value;
-  else if (k == "pipe_producers") ctx->pipe_producers = value;
-  else if (k == "pipe_consumers") ctx->pipe_consumers = value;
   else if (k == "prefetch_dist") ctx->prefetch_dist = value;
   else if (k == "median_ksize") {
     if (value < 1 || value > 15 || !(value & 1)) return D2PC_ERR_INVALID_ARG;
@@ -820,12 +810,10 @@ static int reproject_device_common(d2pc_ctx *ctx, const void *d_in, bool is_f32,
   int rc;
   if (compact) {
     const size_t need = reproject_scratch_bytes(n_frames, w, h, ctx->cfg.border);
-    const size_t need_cells = reproject_cells_bytes(n_frames, w, h, ctx->cfg.border);
-    if (need > ctx->d_scratch.cap || reproject_table_bytes(w, h) > ctx->d_tables.cap || need_cells > ctx->d_cells.cap) {
+    if (need > ctx->d_scratch.cap || reproject_table_bytes(w, h) > ctx->d_tables.cap) {
       CU(ctx, cudaStreamSynchronize(ctx->s_compute));
       if ((rc = grow_dev(ctx, ctx->d_scratch, need, true)) ||
-          (rc = grow_dev(ctx, ctx->d_tables, reproject_table_bytes(w, h))) ||
-          (rc = grow_dev(ctx, ctx->d_cells, need_cells)))
+          (rc = grow_dev(ctx, ctx->d_tables, reproject_table_bytes(w, h))))
         return rc;
     }
   }
@@ -839,7 +827,7 @@ static int reproject_device_common(d2pc_ctx *ctx, const void *d_in, bool is_f32,
     d_med = ctx->d_med_batch.p;
   }
   return enqueue_kernels(ctx, static_cast<const uint8_t *>(d_in), is_f32, n_frames, w, h, step, frame_stride, d_med,
-                         d_points, points_stride, d_counts, ctx->d_scratch.p, ctx->d_tables.p, ctx->d_cells.p, ctx->d_ticket,
+                         d_points, points_stride, d_counts, ctx->d_scratch.p, ctx->d_tables.p, ctx->d_ticket,
                          ctx->s_compute);
 }
 
@@ -1159,11 +1147,10 @@ int d2pc_fuse_then_process(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, 
       (rc = grow_pin(ctx, s.h_out, n * 16 + 16)))
     return rc;
   if (compact && ((rc = grow_dev(ctx, s.d_scratch, reproject_scratch_bytes(1, fw, fh, ctx->cfg.border), true)) ||
-                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(fw, fh))) ||
-                  (rc = grow_dev(ctx, s.d_cells, reproject_cells_bytes(1, fw, fh, ctx->cfg.border)))))
+                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(fw, fh)))))
     return rc;
   rc = enqueue_kernels(ctx, ctx->d_fused.p, false, 1, fw, fh, fw, (size_t)fw * fh, s.d_med.p, s.d_out.p, n * 16 + 16,
-                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_cells.p, s.d_count + 1, ctx->s_compute);
+                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
   if (rc) return rc;
   uint64_t kept = n;
   if (compact) {
@@ -1204,8 +1191,7 @@ int d2pc_submit_fusion(d2pc_ctx *ctx, int slot, const uint8_t *d1, const uint8_t
       (rc = grow_dev(ctx, s.d_out, n * 16 + 16)) || (rc = grow_pin(ctx, s.h_out, n * 16 + 16)))
     return rc;
   if (compact && ((rc = grow_dev(ctx, s.d_scratch, reproject_scratch_bytes(1, fw, fh, c.border), true)) ||
-                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(fw, fh))) ||
-                  (rc = grow_dev(ctx, s.d_cells, reproject_cells_bytes(1, fw, fh, c.border)))))
+                  (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(fw, fh)))))
     return rc;
 
   // ---- H2D (stream 1): pinned caller frames are DMA'd in place, pageable ones are staged
@@ -1238,7 +1224,7 @@ int d2pc_submit_fusion(d2pc_ctx *ctx, int slot, const uint8_t *d1, const uint8_t
                              nullptr, preprocess_scores != 0, &s.d_container)))
     return rc;
   rc = enqueue_kernels(ctx, s.d_fused.p, false, 1, fw, fh, fw, (size_t)fw * fh, s.d_med.p, s.d_out.p, n * 16 + 16, s.d_count,
-                       s.d_scratch.p, s.d_tables.p, s.d_cells.p, s.d_count + 1, ctx->s_compute);
+                       s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
   if (rc) return rc;
   CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
 

@@ -21,8 +21,11 @@
 //   band kernel (default for the stereoRectify form of Q): a CTA owns whole crop rows; TMA bulk row loads,
 //   survivors counted from the disparity alone (four units per REDUX), block scan, ONE decoupled look-back per
 //   band over 64-bit {epoch,flag,value} descriptors, survivors reprojected and stored at offset + ballot rank.
-//   pipeline kernel (opt-in): the same as persistent warp-specialised CTAs (TMA producers / mbarriers).
-//   park / classify-first tile kernels (any Q, FAST mode) and a two-pass count / scan / store variant.
+//   park kernel (any other Q, FAST mode): 32-unit tiles, points parked in shared memory because validity is only
+//   known after the arithmetic, same look-back.
+//   (Round 1 also carried a classify-first tile kernel, a two-pass count / scan / store variant and a
+//   warp-specialised TMA pipeline kernel: all correct, all 1.3-2x slower than the band kernel; removed in round 2,
+//   their measurements are kept in DESIGN.md.)
 #include "reproject.h"
 
 #include <algorithm>
@@ -56,10 +59,6 @@ struct ReprojArgs {
   uint32_t d_sure_bits;       // float bits of the smallest |d| whose point is certainly finite (rect0 compaction)
   int band_rows, cw_pad, band_groups, group_rows;  // band kernel geometry
   int prefetch_dist;          // band kernel: L2 prefetch distance in tiles (0 = off)
-  int pipe_stages;            // pipeline kernel: shared-memory stages (tiles in flight per CTA); 0 = not used
-  int pipe_producers;         // pipeline kernel: producer warps per CTA (1, 2 or 4)
-  int pipe_consumers;         // pipeline kernel: consumer warps per CTA (8: three CTAs per SM, 12: two)
-  uint32_t *cell_cnt;         // two-pass variant: per (frame, row, segment) survivor counts -> exclusive offsets
   QParams Q;
 };
 
@@ -343,185 +342,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(co
 }
 
 // ---------------------------------------------------------------------------
-// CROP_FINITE, two-pass variant (rectified Q with q33 == +-0): count -> scan -> reproject + compacted store
-// ---------------------------------------------------------------------------
-// Whether a point survives is decided by its disparity alone for this Q (see the classify-first kernel below), so
-// a first kernel only READS the disparities and counts the survivors of every (row, 128-column) cell, a small scan
-// kernel turns the counts into output offsets, and the second kernel is the CROP kernel with one change: a cell's
-// survivors are stored from its offset with __ballot_sync + popc ranks.  The disparity is read twice
-// (24 instead of 20 bytes per pixel) but no kernel waits on another CTA and the heavy kernel keeps the CROP
-// kernel's full occupancy and straight-line inner loop.
-__device__ __forceinline__ bool keep_by_disparity(uint32_t mag, uint32_t sure_lo, uint32_t sure_span) {
-  return (mag - sure_lo) < sure_span;  // d_sure <= |d| < inf
-}
-
-template <typename InT, bool kVec>
-__global__ void __launch_bounds__(kThreads, 8) compact_count_kernel(const __grid_constant__ ReprojArgs a) {
-  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const uint32_t unit = blockIdx.x * kWarpsPerCta + wic;
-  if (unit >= a.total_units) return;
-  const uint32_t f = unit / a.units_per_frame;
-  const uint32_t rem = unit - f * a.units_per_frame;
-  const int rb = rem / a.n_seg, seg = rem - rb * a.n_seg;
-  const int c_base = seg * kSegCols, r_base = rb * a.rows_per_unit;
-  const int rows = min(a.rows_per_unit, a.ch - r_base);
-  const uint32_t sure_lo = a.d_sure_bits, sure_span = 0x7f800000u - a.d_sure_bits;
-  const uint8_t *in_row = a.in + (size_t)f * a.frame_stride + (size_t)(a.border + r_base) * a.step;
-  uint32_t *cell = a.cell_cnt + ((size_t)f * a.ch + r_base) * a.n_seg + seg;
-  const int c4 = c_base + 4 * lane;
-  for (int r = 0; r < rows; ++r, in_row += a.step, cell += a.n_seg) {
-    float d[4] = {0.f, 0.f, 0.f, 0.f};  // zero = dropped, also for pixels past the crop edge
-    if constexpr (kVec) {
-      if (c4 < a.cw) {
-        const float4 v = load4<InT>(in_row, a.border + c4, a.scale);
-        d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (c4 + k < a.cw) d[k] = load1<InT>(in_row, a.border + c4 + k, a.scale);
-    }
-    uint32_t cnt = 0;
-    bool sliver = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t mag = (c4 + k < a.cw) ? (__float_as_uint(d[k]) & 0x7fffffffu) : 0u;
-      cnt += keep_by_disparity(mag, sure_lo, sure_span) ? 1u : 0u;
-      sliver |= (mag - 1u) < (sure_lo - 1u);
-    }
-    if (__builtin_expect(sliver, 0)) {  // 0 < |d| < d_sure: decided exactly
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t mag = (c4 + k < a.cw) ? (__float_as_uint(d[k]) & 0x7fffffffu) : 0u;
-        if ((mag - 1u) < (sure_lo - 1u))
-          cnt += point_is_finite(reproject_exact_slow(a.Q.q, a.border + c4 + k, a.border + r_base + r, d[k])) ? 1u : 0u;
-      }
-    }
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (lane == 0) *cell = cnt;
-  }
-}
-
-// Exclusive scan of one frame's cell counts (row-major cells), in place; one CTA per frame, 1024 cells per step.
-__global__ void __launch_bounds__(1024) compact_scan_kernel(uint32_t *cell_cnt, uint32_t cells_per_frame,
-                                                            uint32_t *frame_counts) {
-  __shared__ uint32_t warp_excl[32];
-  __shared__ uint32_t chunk_total;
-  uint32_t *c = cell_cnt + (size_t)blockIdx.x * cells_per_frame;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t carry = 0;  // every thread keeps the same running total
-  for (uint32_t base = 0; base < cells_per_frame; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < cells_per_frame ? c[i] : 0u;
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += n;
-    }
-    if (lane == 31) warp_excl[wid] = incl;  // warp totals
-    __syncthreads();
-    if (wid == 0) {
-      const uint32_t w = warp_excl[lane];
-      uint32_t wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += n;
-      }
-      warp_excl[lane] = wi - w;
-      if (lane == 31) chunk_total = wi;
-    }
-    __syncthreads();
-    if (i < cells_per_frame) c[i] = carry + warp_excl[wid] + incl - v;
-    carry += chunk_total;
-    __syncthreads();  // warp_excl / chunk_total are rewritten by the next step
-  }
-  if (threadIdx.x == 0 && frame_counts) frame_counts[blockIdx.x] = carry;
-}
-
-// The CROP kernel's loop with offset stores: the survivors of cell (row, segment) go to out[offset(cell) + rank].
-template <typename InT, bool kVec>
-__global__ void __launch_bounds__(kThreads, 7) reproject_offsets_kernel(const __grid_constant__ ReprojArgs a) {
-  __shared__ __align__(16) float stage[kWarpsPerCta][2][kSegCols];
-  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const QParams &Q = a.Q;
-  const uint32_t unit = blockIdx.x * kWarpsPerCta + wic;
-  if (unit >= a.total_units) return;
-  const uint32_t f = unit / a.units_per_frame;
-  const uint32_t rem = unit - f * a.units_per_frame;
-  const int rb = rem / a.n_seg, seg = rem - rb * a.n_seg;
-  const int c_base = seg * kSegCols, r_base = rb * a.rows_per_unit;
-  const int rows = min(a.rows_per_unit, a.ch - r_base);
-  const uint32_t sure_lo = a.d_sure_bits, sure_span = 0x7f800000u - a.d_sure_bits;
-
-  double xd[4];
-  uint32_t xslow = Q.zd_slow ? 0xfu : 0u;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    xd[k] = rect_axis_const(a.border + c_base + 32 * k + lane, Q.q03);
-    xslow |= rect_axis_slow(xd[k]) ? (1u << k) : 0u;
-  }
-  const double yd_lane = rect_axis_const(a.border + r_base + lane, Q.q13);
-  const uint8_t *in_row = a.in + (size_t)f * a.frame_stride + (size_t)(a.border + r_base) * a.step;
-  const uint32_t *cell = a.cell_cnt + ((size_t)f * a.ch + r_base) * a.n_seg + seg;  // exclusive offsets now
-  float4 *out_f = a.out + (size_t)f * a.out_frame_stride;
-
-  for (int r = 0; r < rows; r += 2, in_row += 2 * a.step, cell += 2 * a.n_seg) {
-    float dd[2][4];
-    if constexpr (kVec) {
-      const int c4 = c_base + 4 * lane;
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        *reinterpret_cast<float4 *>(&stage[wic][j][4 * lane]) =
-            (r + j < rows && c4 < a.cw) ? load4<InT>(in_row + (size_t)j * a.step, a.border + c4, a.scale)
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dd[j][k] = stage[wic][j][32 * k + lane];
-      __syncwarp();
-    } else {
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = c_base + 32 * k + lane;
-          dd[j][k] = (r + j < rows && c < a.cw) ? load1<InT>(in_row + (size_t)j * a.step, a.border + c, a.scale) : 0.0f;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (r + j >= rows) break;
-      const double yd = __shfl_sync(0xffffffffu, yd_lane, r + j);
-      float4 p[4];
-      points_of4<kMathRect0>(Q, xd, yd, xslow, rect_axis_slow(yd), a.border + c_base + lane, a.border + r_base + r + j,
-                             dd[j], p);
-      bool kp[4], any_sliver = false;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool in_crop = c_base + 32 * k + lane < a.cw;  // the vector tail may hold real pixels past the crop
-        const uint32_t mag = in_crop ? (__float_as_uint(dd[j][k]) & 0x7fffffffu) : 0u;
-        kp[k] = keep_by_disparity(mag, sure_lo, sure_span);
-        any_sliver |= (mag - 1u) < (sure_lo - 1u);
-      }
-      if (__builtin_expect(any_sliver, 0)) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool in_crop = c_base + 32 * k + lane < a.cw;
-          if (in_crop && ((__float_as_uint(dd[j][k]) & 0x7fffffffu) - 1u) < (sure_lo - 1u)) kp[k] = point_is_finite(p[k]);
-        }
-      }
-      uint32_t pos = cell[(size_t)j * a.n_seg];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) pos = store_ranked(out_f, pos, p[k], kp[k], lane, lt_mask);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
 // CROP_FINITE kernel: order-preserving stream compaction, decoupled look-back
 // ---------------------------------------------------------------------------
 // A work unit is one crop row x 128 columns (one warp, 4 pixels per lane, same load + transpose as the CROP
@@ -732,195 +552,17 @@ __global__ void __launch_bounds__(kCThreads, 4) reproject_compact_kernel(const _
 }
 
 // ---------------------------------------------------------------------------
-// CROP_FINITE, rectified Q with q33 == +-0 (the stereoRectify form): classify first, reproject after
-// ---------------------------------------------------------------------------
-// For this Q, whether a point is finite is decided by the disparity alone for all but a sliver of inputs:
-//   d == +-0, inf, NaN            -> W is +0 / NaN: the point is never finite              (dropped)
-//   |d| >= d_sure (normal float)  -> |n / (q32*d)| < 2^127 for every numerator in the frame (kept); d_sure is
-//                                    computed on the host from max |numerator| and |q32|
-//   anything else (denormal, or |d| < d_sure ~ 2^-117)  -> decided by the exact slow path  (rare)
-// So the tile is counted before any FP64 work, the look-back latency overlaps other CTAs, and the survivors are
-// reprojected straight into their final place: no parking of points, 4 KB of shared memory per CTA.
-template <typename InT, bool kVec, int kMinB>
-__global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_rect0_kernel(const __grid_constant__ ReprojArgs a) {
-  __shared__ __align__(16) float stage[kCWarps * kSegCols];
-  __shared__ uint32_t unit_cnt[kTileUnits];
-  __shared__ uint32_t lb_sum[kCWarps], lb_hit[kCWarps];
-  __shared__ uint32_t s_tile;
-  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const QParams &Q = a.Q;
-
-  if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const uint32_t f = tile / a.tiles_per_frame;
-  const uint32_t t_in_f = tile - f * a.tiles_per_frame;
-  const uint8_t *in_f = a.in + (size_t)f * a.frame_stride;
-
-  // ---- this warp's kCIter units: (row, segment) of unit t*32 + 8m + w, stepping by 8 units (one division only)
-  int crow[kCIter], c_base[kCIter];
-  uint32_t cmask = 0;  // bit 4m+k: pixel slot k of unit m lies inside the crop
-  {
-    const uint32_t unit0 = t_in_f * kTileUnits + wic;
-    int row = (int)(unit0 / (uint32_t)a.n_seg), seg = (int)(unit0 - (uint32_t)row * a.n_seg);
-#pragma unroll
-    for (int m = 0; m < kCIter; ++m) {
-      const bool unit_ok = unit0 + m * kCWarps < a.units_per_frame;
-      crow[m] = unit_ok ? row : -1;
-      c_base[m] = unit_ok ? seg * kSegCols : 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) cmask |= (unit_ok && c_base[m] + 32 * k + lane < a.cw) ? (1u << (4 * m + k)) : 0u;
-      seg += kCWarps;
-      while (seg >= a.n_seg) seg -= a.n_seg, ++row;
-    }
-  }
-  // ---- every load is issued first
-  float dd[kCIter][4];
-  {
-    float4 raw[kCIter];
-#pragma unroll
-    for (int m = 0; m < kCIter; ++m) {
-      const uint8_t *in_row = in_f + (size_t)(a.border + max(crow[m], 0)) * a.step;
-      if constexpr (kVec) {
-        const int c4 = c_base[m] + 4 * lane;
-        raw[m] = (crow[m] >= 0 && c4 < a.cw) ? load4<InT>(in_row, a.border + c4, a.scale) : make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          dd[m][k] = ((cmask >> (4 * m + k)) & 1u) ? load1<InT>(in_row, a.border + c_base[m] + 32 * k + lane, a.scale) : 0.0f;
-      }
-    }
-    if constexpr (kVec) {
-#pragma unroll
-      for (int m = 0; m < kCIter; ++m) {
-        *reinterpret_cast<float4 *>(&stage[wic * kSegCols + 4 * lane]) = raw[m];
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dd[m][k] = stage[wic * kSegCols + 32 * k + lane];
-        __syncwarp();
-      }
-    }
-  }
-  // ---- classify (bit 4m+k of `keep`: this lane's pixel survives); the undecidable sliver is one rare branch
-  uint32_t keep = 0, sliver = 0;
-#pragma unroll
-  for (int m = 0; m < kCIter; ++m)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t mag = __float_as_uint(dd[m][k]) & 0x7fffffffu;
-      keep |= (mag - a.d_sure_bits < 0x7f800000u - a.d_sure_bits) ? (1u << (4 * m + k)) : 0u;  // d_sure <= |d| < inf
-      sliver |= (mag - 1u < a.d_sure_bits - 1u) ? (1u << (4 * m + k)) : 0u;                    // 0 < |d| < d_sure
-    }
-  keep &= cmask;
-  sliver &= cmask;
-  if (__builtin_expect(sliver != 0u, 0)) {
-#pragma unroll
-    for (int m = 0; m < kCIter; ++m)
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if ((sliver >> (4 * m + k)) & 1u) {
-          const float4 p = reproject_exact_slow(Q.q, a.border + c_base[m] + 32 * k + lane, a.border + crow[m], dd[m][k]);
-          keep |= point_is_finite(p) ? (1u << (4 * m + k)) : 0u;
-        }
-  }
-#pragma unroll
-  for (int m = 0; m < kCIter; ++m) {
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cnt += __popc(__ballot_sync(0xffffffffu, (keep >> (4 * m + k)) & 1u));
-    if (lane == 0) unit_cnt[m * kCWarps + wic] = cnt;
-  }
-  __syncthreads();
-  const uint32_t mine = lane < kTileUnits ? unit_cnt[lane] : 0u;
-  uint32_t incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += n;
-  }
-  const uint32_t tile_total = __shfl_sync(0xffffffffu, incl, 31);
-  const uint32_t excl_unit = incl - mine;
-
-  // ---- decoupled look-back, block-wide (see reproject_compact_kernel)
-  unsigned long long *desc = a.tile_desc + tile;
-  uint32_t excl = 0;
-  if (t_in_f == 0) {
-    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, tile_total));
-  } else {
-    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagAggregate, tile_total));
-    int look = (int)t_in_f - 1;
-    for (;;) {
-      const int my = look - (int)threadIdx.x;
-      uint32_t flag = kFlagPrefix, val = 0;
-      if (my >= 0) {
-        unsigned long long dv;
-        do {
-          dv = ld_relaxed_u64(a.tile_desc + (tile - t_in_f) + my);
-        } while ((uint32_t)(dv >> 34) != a.epoch || ((dv >> 32) & 3u) == 0);
-        flag = (uint32_t)(dv >> 32) & 3u;
-        val = (uint32_t)dv;
-      }
-      const uint32_t pmask = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
-      const int stop = pmask ? (__ffs(pmask) - 1) : 32;
-      uint32_t contrib = (lane <= stop) ? val : 0u;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-      if (lane == 0) lb_sum[wic] = contrib, lb_hit[wic] = pmask ? 1u : 0u;
-      __syncthreads();
-      bool done = false;
-#pragma unroll
-      for (int w = 0; w < kCWarps; ++w) {
-        if (!done) {
-          excl += lb_sum[w];
-          done = lb_hit[w] != 0u;
-        }
-      }
-      if (done) break;
-      look -= kCThreads;
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, excl + tile_total));
-  }
-  if (threadIdx.x == 0 && t_in_f == a.tiles_per_frame - 1 && a.counts) a.counts[f] = excl + tile_total;
-
-  // ---- reproject the survivors into their final place; each pixel slot is one contiguous run of points.
-  // The numerator tables hold NaN where the straight-line path must not be used (see rect_tables_kernel).
-  float4 *out_f = a.out + (size_t)f * a.out_frame_stride + excl;
-#pragma unroll
-  for (int m = 0; m < kCIter; ++m) {
-    uint32_t pos = __shfl_sync(0xffffffffu, excl_unit, m * kCWarps + wic);
-    if (crow[m] < 0) continue;  // warp-uniform
-    const int v = a.border + crow[m], u0 = a.border + c_base[m] + lane;
-    double xd[4];
-    uint32_t xslow = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      xd[k] = a.xtab[u0 + 32 * k];  // the table is padded past the image width
-      xslow |= (((uint32_t)__double2hiint(xd[k]) & 0x7ff00000u) == 0x7ff00000u) ? (1u << k) : 0u;
-    }
-    const double yd = a.ytab[v];
-    const bool yslow = ((uint32_t)__double2hiint(yd) & 0x7ff00000u) == 0x7ff00000u;
-    float4 p[4];
-    points_of4<kMathRect0>(Q, xd, yd, xslow, yslow, u0, v, dd[m], p);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool kp = (keep >> (4 * m + k)) & 1u;
-      const uint32_t bal = __ballot_sync(0xffffffffu, kp);
-      if (kp) st_stream_f4(out_f + pos + __popc(bal & lt_mask), p[k]);
-      pos += __popc(bal);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
 // CROP_FINITE, rectified Q with q33 == +-0: band kernel (the default for this Q)
 // ---------------------------------------------------------------------------
 // One CTA owns a band of R full crop rows (a contiguous range of the frame's point order):
 //   1. the band's disparities are brought into shared memory once with 16-byte cp.async (zero-filled past the
 //      crop edge, so padding classifies as "dropped" without any mask);
-//   2. every (row, 128-column) unit is classified from the disparity alone (see the classify-first kernel
-//      above for the three classes) and counted with __ballot_sync + popc -- no FP64 work yet;
+//   2. every (row, 128-column) unit is classified from the disparity alone and counted -- no FP64 work yet.  For
+//      this Q whether a point is finite is decided by the disparity for all but a sliver of inputs:
+//        d == +-0, inf, NaN            -> W is +0 / NaN: the point is never finite              (dropped)
+//        |d| >= d_sure (normal float)  -> |n / (q32*d)| < 2^127 for every numerator in the frame (kept); d_sure is
+//                                         computed on the host from max |numerator| and |q32|
+//        anything else (denormal, or |d| < d_sure ~ 2^-117)  -> decided by the exact slow path  (rare);
 //   3. block scan of the unit counts -> unit offsets and the band total;
 //   4. ONE decoupled look-back per band (block-wide, 256 predecessors per step);
 //   5. warps sweep (segment, row-group) items: column numerators live in registers across the rows of the item,
@@ -929,7 +571,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_rect0_kern
 constexpr int kBandMaxUnits = 512;
 constexpr int kBandMaxRows = 16;
 
-// ---- mbarrier / TMA bulk-copy helpers (band and pipeline kernels)
+// ---- mbarrier / TMA bulk-copy helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -982,13 +624,15 @@ __device__ __forceinline__ void cp_async_16_zfill(void *smem_dst, const void *gm
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 
-template <typename InT, bool kVec, int kMinB>
-__global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kernel(const __grid_constant__ ReprojArgs a) {
+// kW warps per CTA (8 is what ships: four 46 KB CTAs per SM).
+template <typename InT, bool kVec, int kMinB, int kW>
+__global__ void __launch_bounds__(kW * 32, kMinB) reproject_compact_band_kernel(const __grid_constant__ ReprojArgs a) {
+  constexpr int kT = kW * 32;
   extern __shared__ __align__(16) float sd[];  // [band_rows][cw_pad]
   __shared__ uint32_t unit_off[kBandMaxUnits];
   __shared__ double syd[kBandMaxRows];
-  __shared__ uint32_t warp_tot[kCWarps];
-  __shared__ uint32_t lb_sum[kCWarps], lb_hit[kCWarps];
+  __shared__ uint32_t warp_tot[kW];
+  __shared__ uint32_t lb_sum[kW], lb_hit[kW];
   __shared__ uint32_t s_tile;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -1037,19 +681,19 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
       }
     }
     const int pad4 = (cwp - cw4) >> 2;  // float4 groups of padding per row
-    for (int t = (int)threadIdx.x; t < pad4 * rows_here; t += kCThreads) {
+    for (int t = (int)threadIdx.x; t < pad4 * rows_here; t += kT) {
       const int r = t / pad4, g4 = t - r * pad4;
       *reinterpret_cast<float4 *>(&sd[r * cwp + cw4 + 4 * g4]) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int t = (int)threadIdx.x; t < (R - rows_here) * (cwp >> 2); t += kCThreads)
+    for (int t = (int)threadIdx.x; t < (R - rows_here) * (cwp >> 2); t += kT)
       *reinterpret_cast<float4 *>(&sd[rows_here * cwp + 4 * t]) = make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(&bar_rows, 0);
     if (a.cw & 3)  // the copy brought up to 3 real pixels past the crop edge: they must not be counted or kept
-      for (int t = (int)threadIdx.x; t < rows_here * 4; t += kCThreads)
+      for (int t = (int)threadIdx.x; t < rows_here * 4; t += kT)
         if ((t & 3) >= (a.cw & 3)) sd[(t >> 2) * cwp + (a.cw & ~3) + (t & 3)] = 0.f;
   }
   // (cp.async / scalar staging for unaligned or mono8 rows: columns outer, rows inner)
-  for (int c4 = 4 * (int)threadIdx.x; !kTma && c4 < cwp; c4 += 4 * kCThreads) {
+  for (int c4 = 4 * (int)threadIdx.x; !kTma && c4 < cwp; c4 += 4 * kT) {
     const int left = min(max(a.cw - c4, 0), 4);  // crop pixels this 4-pixel group holds
     float *dst = &sd[c4];
     if constexpr (kVec && sizeof(InT) == 4) {
@@ -1088,7 +732,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
   // The band is a flat array of units (cw_pad = n_seg * 128, so unit u starts at float 128 * u).  A warp takes
   // four consecutive units at a time; each lane counts its 4 pixels of every unit into one byte of a word and a
   // single REDUX adds all four units at once (a unit has 128 pixels, so no byte can carry into the next).
-  for (int u0 = 4 * wic; u0 < n_units; u0 += 4 * kCWarps) {
+  for (int u0 = 4 * wic; u0 < n_units; u0 += 4 * kW) {
     uint32_t packed = 0;
     bool rare = false;
 #pragma unroll
@@ -1122,12 +766,18 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
     if (lane < 4 && u0 + lane < n_units) unit_off[u0 + lane] = (packed >> (8 * lane)) & 0xffu;
   }
   __syncthreads();
-  // ---- 3. exclusive scan of the unit counts (two entries per thread)
+  // ---- 3. exclusive scan of the unit counts (kE consecutive entries per thread)
   uint32_t band_total;
   {
-    const int i0 = 2 * (int)threadIdx.x;
-    const uint32_t c0 = i0 < n_units ? unit_off[i0] : 0u, c1 = i0 + 1 < n_units ? unit_off[i0 + 1] : 0u;
-    uint32_t incl = c0 + c1;
+    constexpr int kE = kBandMaxUnits / kT;
+    const int i0 = kE * (int)threadIdx.x;
+    uint32_t c[kE], sum = 0;
+#pragma unroll
+    for (int e = 0; e < kE; ++e) {
+      c[e] = i0 + e < n_units ? unit_off[i0 + e] : 0u;
+      sum += c[e];
+    }
+    uint32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
@@ -1137,15 +787,18 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
     __syncthreads();
     uint32_t wbase = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < kCWarps; ++w) {
+    for (int w = 0; w < kW; ++w) {
       const uint32_t t = warp_tot[w];
       wbase += (w < wic) ? t : 0u;
       tot += t;
     }
     band_total = tot;
-    const uint32_t e0 = wbase + incl - (c0 + c1);
-    if (i0 < n_units) unit_off[i0] = e0;
-    if (i0 + 1 < n_units) unit_off[i0 + 1] = e0 + c0;
+    uint32_t run = wbase + incl - sum;
+#pragma unroll
+    for (int e = 0; e < kE; ++e) {
+      if (i0 + e < n_units) unit_off[i0 + e] = run;
+      run += c[e];
+    }
   }
   // ---- 4. decoupled look-back, block-wide; the first band of a frame starts the chain
   unsigned long long *desc = a.tile_desc + tile;
@@ -1176,14 +829,14 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
       __syncthreads();
       bool done = false;
 #pragma unroll
-      for (int w = 0; w < kCWarps; ++w) {
+      for (int w = 0; w < kW; ++w) {
         if (!done) {
           excl += lb_sum[w];
           done = lb_hit[w] != 0u;
         }
       }
       if (done) break;
-      look -= kCThreads;
+      look -= kT;
       __syncthreads();
     }
     if (threadIdx.x == 0) st_relaxed_u64(desc, desc_pack(a.epoch, kFlagPrefix, excl + band_total));
@@ -1193,7 +846,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
   // ---- 5. reproject + store: item = (segment, row group); column numerators stay in registers over its rows
   float4 *out_f = a.out + (size_t)f * a.out_frame_stride + excl;
   const int n_items = n_seg * a.band_groups;
-  for (int item = wic; item < n_items; item += kCWarps) {
+  for (int item = wic; item < n_items; item += kW) {
     const int g = item / n_seg, sgm = item - g * n_seg;
     const int r_lo = g * a.group_rows, r_hi = min(r_lo + a.group_rows, R);
     const int u0 = a.border + sgm * kSegCols + lane;
@@ -1230,348 +883,6 @@ __global__ void __launch_bounds__(kCThreads, kMinB) reproject_compact_band_kerne
 }
 
 
-// ---------------------------------------------------------------------------
-// CROP_FINITE, rectified Q with q33 == +-0, float32 rows, 16-byte aligned: warp-specialised pipeline kernel
-// ---------------------------------------------------------------------------
-// Same decomposition as the band kernel (a tile = R full crop rows, classify from the disparity, one look-back per
-// tile, survivors reprojected straight into place) but the phases run on different warps of a PERSISTENT CTA and
-// are decoupled by mbarriers, so no warp that does arithmetic ever waits for HBM or for another CTA:
-//   producer warps  claim a tile (atomic ticket), bring its rows into a shared-memory stage with TMA bulk copies
-//                   (cp.async.bulk, completion on an mbarrier), count the survivors of every (row, 128-column)
-//                   unit, scan the counts, publish the tile aggregate, run the decoupled look-back and hand the
-//                   stage to the consumers ("ready" mbarrier); loads for the next stages are already in flight;
-//   consumer warps  take (segment x rows) items of ready stages in a rotating order, reproject from shared memory
-//                   and store survivors at unit_offset + rank (ballot + popc); a stage returns to the producer
-//                   when all consumer warps have arrived on its "empty" mbarrier.
-// A producer only waits for consumers BEFORE it claims a ticket; once a tile is claimed its aggregate and prefix
-// are published without depending on any consumer, so the look-back chain always makes progress.
-constexpr int kPipeMaxStages = 12;
-constexpr int kPipeMaxUnits = 128;  // units per tile
-constexpr int kPipeMaxRows = 16;
-constexpr uint32_t kPipeNoTile = 0xffffffffu;
-
-struct PipeStageInfo {
-  uint32_t tile, excl, frame, rows, total;
-  int row0;
-};
-
-// Survivors of one (row, 128-column) unit, counted from the disparities alone (4 adjacent pixels per lane).
-__device__ __forceinline__ uint32_t count_unit_rect0(const QParams &Q, const float *unit, int lane, int u_base, int v,
-                                                    uint32_t sure_lo, uint32_t sure_span) {
-  const float4 d4 = *reinterpret_cast<const float4 *>(&unit[4 * lane]);
-  const uint32_t m0 = __float_as_uint(d4.x) & 0x7fffffffu, m1 = __float_as_uint(d4.y) & 0x7fffffffu;
-  const uint32_t m2 = __float_as_uint(d4.z) & 0x7fffffffu, m3 = __float_as_uint(d4.w) & 0x7fffffffu;
-  // sure class: d_sure <= |d| < inf
-  uint32_t cnt = ((m0 - sure_lo) < sure_span) + ((m1 - sure_lo) < sure_span) + ((m2 - sure_lo) < sure_span) +
-                 ((m3 - sure_lo) < sure_span);
-  // sliver class 0 < |d| < d_sure: decided exactly, rare
-  if (__builtin_expect(min(min(m0 - 1u, m1 - 1u), min(m2 - 1u, m3 - 1u)) < sure_lo - 1u, 0)) {
-    const int u = u_base + 4 * lane;
-    if ((m0 - 1u) < (sure_lo - 1u)) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 0, v, d4.x)) ? 1u : 0u;
-    if ((m1 - 1u) < (sure_lo - 1u)) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 1, v, d4.y)) ? 1u : 0u;
-    if ((m2 - 1u) < (sure_lo - 1u)) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 2, v, d4.z)) ? 1u : 0u;
-    if ((m3 - 1u) < (sure_lo - 1u)) cnt += point_is_finite(reproject_exact_slow(Q.q, u + 3, v, d4.w)) ? 1u : 0u;
-  }
-  return __reduce_add_sync(0xffffffffu, cnt);
-}
-
-template <int kPW, int kCW>
-__global__ void __launch_bounds__((kCW + kPW) * 32, (kCW + kPW) * 32 <= 384 ? 3 : 2)
-    reproject_compact_pipe_kernel(const __grid_constant__ ReprojArgs a) {
-  extern __shared__ __align__(128) float pipe_stage[];  // [stages][R][cw_pad]
-  __shared__ __align__(8) unsigned long long bar_full[kPipeMaxStages], bar_ready[kPipeMaxStages], bar_empty[kPipeMaxStages];
-  __shared__ PipeStageInfo info[kPipeMaxStages];
-  __shared__ __align__(16) uint32_t unit_off[kPipeMaxStages][kPipeMaxUnits];
-  __shared__ double syd[kPipeMaxStages][kPipeMaxRows];
-  __shared__ uint32_t p_issued, p_flags;
-  __shared__ uint32_t lb_sum[kPW], lb_hit[kPW];
-
-  const QParams &Q = a.Q;
-  const int B = a.pipe_stages, R = a.band_rows, cwp = a.cw_pad, n_seg = a.n_seg;
-  const uint32_t stage_floats = (uint32_t)R * (uint32_t)cwp;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t sure_lo = a.d_sure_bits, sure_span = 0x7f800000u - a.d_sure_bits;
-
-  // every stage starts zeroed: TMA only ever writes columns [0, roundup4(cw)) of a row, so the padding up to
-  // cw_pad classifies as "dropped" for the whole kernel
-  for (uint32_t i = threadIdx.x; i < (uint32_t)B * stage_floats / 4; i += blockDim.x)
-    reinterpret_cast<float4 *>(pipe_stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (threadIdx.x == 0) {
-    for (int b = 0; b < B; ++b) {
-      mbar_init(&bar_full[b], 1);
-      mbar_init(&bar_ready[b], 1);
-      mbar_init(&bar_empty[b], kCW);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  fence_proxy_async_smem();  // the zeroing (generic proxy) is ordered before the first TMA write (async proxy)
-  __syncthreads();
-
-  if (warp >= kCW) {
-    // =========================== producer group: issue, count, look-back ===========================
-    constexpr int kPT = kPW * 32;
-    const int ptid = (int)threadIdx.x - kCW * 32, pw = warp - kCW;
-    auto group_sync = [&]() {
-      if constexpr (kPW == 1) __syncwarp();
-      else asm volatile("bar.sync 1, %0;" ::"n"(kPT) : "memory");
-    };
-    const uint32_t total_tiles = a.tiles_per_frame * (uint32_t)a.n_frames;
-    const uint32_t row_copy_bytes = (uint32_t)((a.cw + 3) & ~3) * 4u;
-    // Three cursors over this CTA's tiles (the end marker counts as one): i issued (ticket claimed, TMA in
-    // flight), c scanned (the consumers' unit counts turned into offsets, aggregate published), j resolved
-    // (look-back done, handed to the consumers); j <= c <= i <= j + B.  Scanning runs ahead of resolving so that
-    // a tile's aggregate is public as soon as it has been counted -- other CTAs' look-backs never wait behind
-    // this CTA's own look-back.
-    uint32_t i = 0, c = 0, j = 0;
-    uint32_t bi = 0, use_i = 0, bc = 0, use_c = 0, bj = 0, use_j = 0;  // stage index / earlier uses of it, per cursor
-    bool exhausted = false, pending = false;
-    uint32_t pending_tile = 0;
-    for (;;) {
-      if (ptid == 0) {
-        // The ticket's round trip (an L2 atomic) is taken off the critical path: it is claimed once its stage is
-        // known to be free, and the rows are put in flight at the top of the NEXT step, when the value has
-        // arrived.  (A ticket is never held while waiting for a stage: that would stall every later tile.)
-        for (;;) {
-          if (pending) {
-            const uint32_t tile = pending_tile;
-            if (tile >= total_tiles) {
-              exhausted = true;
-              info[bi].tile = kPipeNoTile;
-            } else {
-              const uint32_t f = tile / a.tiles_per_frame, t_in_f = tile - f * a.tiles_per_frame;
-              const int row0 = (int)t_in_f * R, rows = min(R, a.ch - row0);
-              info[bi].tile = tile;
-              info[bi].frame = f;
-              info[bi].row0 = row0;
-              info[bi].rows = (uint32_t)rows;
-              mbar_arrive_expect_tx(&bar_full[bi], (uint32_t)rows * row_copy_bytes);
-              const uint8_t *src = a.in + (size_t)f * a.frame_stride + (size_t)(a.border + row0) * a.step + (size_t)a.border * 4;
-              const uint32_t dst = smem_u32(pipe_stage + (size_t)bi * stage_floats);
-              for (int r = 0; r < rows; ++r)
-                tma_load_1d(dst + (uint32_t)r * (uint32_t)cwp * 4u, src + (size_t)r * a.step, row_copy_bytes, &bar_full[bi]);
-            }
-            pending = false;
-            ++i;
-            if (++bi == (uint32_t)B) bi = 0, ++use_i;
-          }
-          if (exhausted || i >= j + (uint32_t)B) break;
-          if (use_i > 0) {  // the stage must have been drained by the consumers
-            const uint32_t par = (use_i - 1u) & 1u;
-            if (i == j) mbar_wait(&bar_empty[bi], par);            // nothing else to do: block
-            else if (!mbar_test_wait(&bar_empty[bi], par)) break;  // count / resolve something first
-          }
-          pending_tile = atomicAdd(a.ticket, 1u);
-          pending = true;
-          if (i != j) break;  // there is other work: pick the value up at the top of the next step
-        }
-        // next step: count the oldest uncounted tile if its rows have landed (or nothing is left to resolve)
-        uint32_t scan_next = 0;
-        if (c < i)
-          scan_next = (c == j || info[bc].tile == kPipeNoTile || mbar_test_wait(&bar_full[bc], use_c & 1u)) ? 1u : 0u;
-        p_issued = i;
-        p_flags = (exhausted ? 1u : 0u) | (scan_next << 1) | (pending ? 4u : 0u);
-      }
-      group_sync();
-      i = p_issued;
-      exhausted = (p_flags & 1u) != 0u;
-      const uint32_t p_flags_copy = p_flags;
-      const bool scan_next = (p_flags_copy & 2u) != 0u;
-      group_sync();  // p_issued / p_flags are rewritten at the top of the next iteration
-      if (j == i && (p_flags_copy & 4u) == 0u) break;  // (only once the tickets are exhausted)
-      if (scan_next) {
-        // ---- tile c: unit counts -> unit offsets, publish the aggregate
-        const uint32_t tile = info[bc].tile;
-        if (tile != kPipeNoTile) {
-          mbar_wait(&bar_full[bc], use_c & 1u);
-          const uint32_t f = info[bc].frame;
-          const int row0 = info[bc].row0, rows = (int)info[bc].rows;
-          const uint32_t t_in_f = tile - f * a.tiles_per_frame;
-          float *sd = pipe_stage + (size_t)bc * stage_floats;
-          if (a.cw & 3) {  // the copy brought up to 3 real pixels past the crop edge: they must not be counted
-            for (int t = ptid; t < rows * 4; t += kPT)
-              if ((t & 3) >= (a.cw & 3)) sd[(t >> 2) * cwp + (a.cw & ~3) + (t & 3)] = 0.f;
-            fence_proxy_async_smem();
-            group_sync();
-          }
-          if (ptid >= kPT - rows) {  // row numerators (last lanes of the group); NaN marks a row the straight-line
-            const int r = kPT - 1 - ptid;  // path must not use
-            const double y = rect_axis_const(a.border + row0 + r, Q.q13);
-            syd[bc][r] = rect_axis_slow(y) ? __longlong_as_double(0x7ff8000000000000ll) : y;
-          }
-          // survivors per unit from the disparity alone.  The stage is a flat array of units (cw_pad = n_seg * 128,
-          // so unit u starts at float 128 * u); a warp takes four consecutive units at a time, each lane counts
-          // its 4 pixels of every unit into one byte of a word, and a single REDUX adds all four units at once
-          // (a unit has 128 pixels, so no byte can carry into the next).
-          {
-            const int n_units = rows * n_seg;
-            for (int u0 = 4 * pw; u0 < n_units; u0 += 4 * kPW) {
-              uint32_t packed = 0;
-              bool rare = false;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (u0 + q < n_units) {
-                  const float4 d4 = *reinterpret_cast<const float4 *>(&sd[(u0 + q) * kSegCols + 4 * lane]);
-                  const uint32_t m0 = __float_as_uint(d4.x) & 0x7fffffffu, m1 = __float_as_uint(d4.y) & 0x7fffffffu;
-                  const uint32_t m2 = __float_as_uint(d4.z) & 0x7fffffffu, m3 = __float_as_uint(d4.w) & 0x7fffffffu;
-                  const uint32_t cq = ((m0 - sure_lo) < sure_span) + ((m1 - sure_lo) < sure_span) +
-                                      ((m2 - sure_lo) < sure_span) + ((m3 - sure_lo) < sure_span);
-                  rare |= min(min(m0 - 1u, m1 - 1u), min(m2 - 1u, m3 - 1u)) < sure_lo - 1u;  // sliver 0 < |d| < d_sure
-                  packed |= cq << (8 * q);
-                }
-              }
-              if (__builtin_expect(rare, 0)) {  // slivers are decided by the exact path
-#pragma unroll 1
-                for (int q = 0; q < 4 && u0 + q < n_units; ++q) {
-                  const int r = (u0 + q) / n_seg, sgm = (u0 + q) - r * n_seg;
-                  const float *px = &sd[(u0 + q) * kSegCols + 4 * lane];
-#pragma unroll 1
-                  for (int e = 0; e < 4; ++e) {
-                    const uint32_t m = __float_as_uint(px[e]) & 0x7fffffffu;
-                    if ((m - 1u) < (sure_lo - 1u) &&
-                        point_is_finite(reproject_exact_slow(Q.q, a.border + sgm * kSegCols + 4 * lane + e,
-                                                             a.border + row0 + r, px[e])))
-                      packed += 1u << (8 * q);
-                  }
-                }
-              }
-              packed = __reduce_add_sync(0xffffffffu, packed);
-              if (lane < 4 && u0 + lane < n_units) unit_off[bc][u0 + lane] = (packed >> (8 * lane)) & 0xffu;
-            }
-          }
-          group_sync();
-          if (pw == 0) {  // exclusive scan of <= 128 unit counts, four per lane
-            const int n_units = rows * n_seg;
-            uint4 u4 = *reinterpret_cast<const uint4 *>(&unit_off[bc][4 * lane]);
-            if (4 * lane + 0 >= n_units) u4.x = 0;
-            if (4 * lane + 1 >= n_units) u4.y = 0;
-            if (4 * lane + 2 >= n_units) u4.z = 0;
-            if (4 * lane + 3 >= n_units) u4.w = 0;
-            const uint32_t mine = u4.x + u4.y + u4.z + u4.w;
-            uint32_t incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += n;
-            }
-            const uint32_t e0 = incl - mine;
-            *reinterpret_cast<uint4 *>(&unit_off[bc][4 * lane]) =
-                make_uint4(e0, e0 + u4.x, e0 + u4.x + u4.y, e0 + u4.x + u4.y + u4.z);
-            if (lane == 31) {
-              info[bc].total = incl;
-              // the first tile of a frame starts the chain: its aggregate is its inclusive prefix
-              st_relaxed_u64(a.tile_desc + tile, desc_pack(a.epoch, t_in_f == 0 ? kFlagPrefix : kFlagAggregate, incl));
-            }
-          }
-        }
-        ++c;
-        if (++bc == (uint32_t)B) bc = 0, ++use_c;
-        continue;  // (the group_sync at the top of the loop orders unit_off / info / syd before any later use)
-      }
-      // ---- resolve tile j: decoupled look-back over the earlier tiles of its frame, kPT predecessors per step
-      const uint32_t tile = info[bj].tile;
-      if (tile == kPipeNoTile) {  // end marker: release the consumers
-        if (ptid == 0) mbar_arrive(&bar_ready[bj]);
-        break;
-      }
-      const uint32_t f = info[bj].frame, tile_total = info[bj].total;
-      const uint32_t t_in_f = tile - f * a.tiles_per_frame;
-      uint32_t excl = 0;
-      if (t_in_f != 0) {
-        int look = (int)t_in_f - 1;
-        for (;;) {
-          const int my = look - ptid;
-          uint32_t flag = kFlagPrefix, val = 0;  // positions before the frame start act as a zero prefix
-          if (my >= 0) {
-            unsigned long long dv;
-            do {
-              dv = ld_relaxed_u64(a.tile_desc + (tile - t_in_f) + my);
-            } while ((uint32_t)(dv >> 34) != a.epoch || ((dv >> 32) & 3u) == 0);
-            flag = (uint32_t)(dv >> 32) & 3u;
-            val = (uint32_t)dv;
-          }
-          const uint32_t pmask = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
-          const int stop = pmask ? (__ffs(pmask) - 1) : 32;
-          uint32_t contrib = (lane <= stop) ? val : 0u;
-          contrib = __reduce_add_sync(0xffffffffu, contrib);
-          bool done;
-          if constexpr (kPW == 1) {
-            excl += contrib;
-            done = pmask != 0u;
-          } else {
-            if (lane == 0) lb_sum[pw] = contrib, lb_hit[pw] = pmask ? 1u : 0u;
-            group_sync();
-            done = false;
-#pragma unroll
-            for (int w = 0; w < kPW; ++w)
-              if (!done) {
-                excl += lb_sum[w];
-                done = lb_hit[w] != 0u;
-              }
-            group_sync();  // lb_* are rewritten by the next step / the next tile
-          }
-          if (done) break;
-          look -= kPT;
-        }
-        if (ptid == 0) st_relaxed_u64(a.tile_desc + tile, desc_pack(a.epoch, kFlagPrefix, excl + tile_total));
-      }
-      if (ptid == 0) {
-        if (t_in_f == a.tiles_per_frame - 1 && a.counts) a.counts[f] = excl + tile_total;
-        info[bj].excl = excl;
-        mbar_arrive(&bar_ready[bj]);  // release: unit_off, syd, info are visible to the waiting consumers
-      }
-      ++j;
-      if (++bj == (uint32_t)B) bj = 0, ++use_j;
-    }
-  } else {
-    // =========================== consumers: reproject + store ===========================
-    const int wic = warp;
-    const uint32_t fast_span = max(min(Q.dhi_bits, 0x7f800000u), sure_lo) - sure_lo;
-    uint32_t bj = 0, use_j = 0;
-    uint32_t g = (uint32_t)wic, base = 0;  // this warp's next item / first item of the current tile, numbered over
-                                           // all tiles of the CTA so that the warps rotate over the segments
-    for (;;) {
-      mbar_wait_backoff(&bar_ready[bj], use_j & 1u);
-      const uint32_t tile = info[bj].tile;
-      if (tile == kPipeNoTile) break;
-      mbar_wait(&bar_full[bj], use_j & 1u);  // (complete long ago: makes the TMA writes visible to this thread)
-      const uint32_t f = info[bj].frame, excl = info[bj].excl;
-      const int row0 = info[bj].row0, rows = (int)info[bj].rows;
-      float4 *out_f = a.out + (size_t)f * a.out_frame_stride + excl;
-      const float *sd = pipe_stage + (size_t)bj * stage_floats;
-      while (g < base + (uint32_t)n_seg) {
-        const int sgm = (int)(g - base);
-        const int u0 = a.border + sgm * kSegCols + lane;
-        double xd[4];
-        bool xslow = Q.zd_slow != 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          xd[k] = __ldg(&a.xtab[u0 + 32 * k]);  // NaN marks a column the straight-line path must not use
-          xslow |= ((uint32_t)__double2hiint(xd[k]) & 0x7ff00000u) == 0x7ff00000u;
-        }
-        for (int r = 0; r < rows; ++r) {
-          const double yd = syd[bj][r];
-          const bool yslow = ((uint32_t)__double2hiint(yd) & 0x7ff00000u) == 0x7ff00000u;
-          const float *dp = &sd[r * cwp + sgm * kSegCols + lane];
-          float dd[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dd[k] = dp[32 * k];
-          float4 p[4];
-          bool kp[4];
-          points_of4_keep(Q, xd, yd, yslow || xslow, u0, a.border + row0 + r, dd, sure_lo, fast_span, p, kp);
-          uint32_t pos = unit_off[bj][r * n_seg + sgm];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) pos = store_ranked_tight(out_f, pos, p[k], kp[k]);
-        }
-        g += kCW;
-      }
-      base += (uint32_t)n_seg;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_empty[bj]);
-      if (++bj == (uint32_t)B) bj = 0, ++use_j;
-    }
-  }
-}
-
 template <typename K>
 cudaError_t launch_compact(K kernel, const ReprojArgs &a, int grid, cudaStream_t s) {
   // 52 KB of dynamic shared memory needs the opt-in on every instantiation (and on every device)
@@ -1584,44 +895,17 @@ cudaError_t launch_compact(K kernel, const ReprojArgs &a, int grid, cudaStream_t
 template <typename InT, int kMath>
 cudaError_t launch_typed(const ReprojArgs &a, bool vec, bool compact, int grid, int min_blocks, cudaStream_t s) {
   if (compact) {
-    if constexpr (kMath == kMathRect0 && sizeof(InT) == 4) {
-      if (a.pipe_stages > 0) {  // warp-specialised pipeline kernel
-        const size_t smem = (size_t)a.pipe_stages * a.band_rows * a.cw_pad * sizeof(float);
-        auto kern = reproject_compact_pipe_kernel<2, 8>;  // 320 threads, three CTAs per SM
-        int threads = 320;
-        switch (a.pipe_producers * 100 + a.pipe_consumers) {
-          case 108: kern = reproject_compact_pipe_kernel<1, 8>, threads = 288; break;
-          case 408: kern = reproject_compact_pipe_kernel<4, 8>, threads = 384; break;
-          case 212: kern = reproject_compact_pipe_kernel<2, 12>, threads = 448; break;  // two CTAs per SM
-          case 412: kern = reproject_compact_pipe_kernel<4, 12>, threads = 512; break;
-          default: break;
-        }
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, threads, smem, s>>>(a);
-        return cudaGetLastError();
-      }
-    }
     if constexpr (kMath == kMathRect0) {
       if (a.d_sure_bits != 0 && a.band_rows > 0) {  // band kernel
         const size_t smem = (size_t)a.band_rows * a.cw_pad * sizeof(float);
-        auto kern = !vec ? reproject_compact_band_kernel<InT, false, 3>
-                         : (min_blocks == 3 ? reproject_compact_band_kernel<InT, true, 3>
-                                            : reproject_compact_band_kernel<InT, true, 4>);
+        auto kern = !vec ? reproject_compact_band_kernel<InT, false, 3, 8>
+                         : (min_blocks == 3 ? reproject_compact_band_kernel<InT, true, 3, 8>
+                                            : reproject_compact_band_kernel<InT, true, 4, 8>);
         if (smem > 48 * 1024) {
           cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           if (e != cudaSuccess) return e;
         }
         kern<<<grid, kCThreads, smem, s>>>(a);
-        return cudaGetLastError();
-      }
-      if (a.d_sure_bits != 0) {  // classify-first kernel
-        if (!vec)
-          reproject_compact_rect0_kernel<InT, false, 3><<<grid, kCThreads, 0, s>>>(a);
-        else if (min_blocks == 3)
-          reproject_compact_rect0_kernel<InT, true, 3><<<grid, kCThreads, 0, s>>>(a);
-        else
-          reproject_compact_rect0_kernel<InT, true, 4><<<grid, kCThreads, 0, s>>>(a);
         return cudaGetLastError();
       }
     }
@@ -1693,15 +977,9 @@ static uint64_t compact_tiles_per_frame(long cw, long ch) {
 // tile descriptors (must start zeroed: epoch 0 means "never written")
 size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border) {
   const long cw = (long)width - 2L * border, ch = (long)height - 2L * border;
-  // enough for either tiling: 32-unit tiles (park / classify-first kernels) or row bands (band kernel)
+  // enough for either tiling: 32-unit tiles (park kernel) or row bands (band kernel)
   const uint64_t tiles = (cw > 0 && ch > 0) ? std::max<uint64_t>(compact_tiles_per_frame(cw, ch), (uint64_t)ch) : 0;
   return (size_t)(tiles * n_frames * 8 + 256);
-}
-// two-pass variant: one uint32 per (frame, crop row, 128-column segment)
-size_t reproject_cells_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border) {
-  const long cw = (long)width - 2L * border, ch = (long)height - 2L * border;
-  if (cw <= 0 || ch <= 0) return 256;
-  return (size_t)n_frames * (size_t)ch * (size_t)((cw + kSegCols - 1) / kSegCols) * 4 + 256;
 }
 // per-column / per-row numerator tables of the rectified path
 size_t reproject_table_bytes(uint32_t width, uint32_t height) { return ((size_t)width + kSegCols + height) * 8 + 64; }
@@ -1779,66 +1057,15 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
         memcpy(&a.d_sure_bits, &fs, 4);
       }
     }
-    if (a.d_sure_bits != 0 && L.compact_variant == 4 && L.cells) {
-      // two-pass variant: count -> scan -> CROP-style kernel with offset stores
-      int rb = 8;
-      const uint64_t want_units = (uint64_t)L.sm_count * 32;
-      while (rb > 2 && (uint64_t)a.n_seg * ((ch + rb - 1) / rb) * L.n_frames < want_units) rb >>= 1;
-      a.rows_per_unit = rb;
-      a.n_rb = (int)((ch + rb - 1) / rb);
-      a.units_per_frame = (uint32_t)a.n_seg * (uint32_t)a.n_rb;
-      const uint64_t total_u = (uint64_t)a.units_per_frame * L.n_frames;
-      if (total_u > 0xffffffffull) return cudaErrorInvalidValue;
-      a.total_units = (uint32_t)total_u;
-      a.cell_cnt = static_cast<uint32_t *>(L.cells);
-      const int g = (int)((total_u + kWarpsPerCta - 1) / kWarpsPerCta);
-      const uint32_t cells_per_frame = (uint32_t)a.n_seg * (uint32_t)ch;
-#define D2PC_TWO_PASS(T)                                                                                   \
-  do {                                                                                                     \
-    if (vec) compact_count_kernel<T, true><<<g, kThreads, 0, stream>>>(a);                                 \
-    else compact_count_kernel<T, false><<<g, kThreads, 0, stream>>>(a);                                    \
-    compact_scan_kernel<<<L.n_frames, 1024, 0, stream>>>(a.cell_cnt, cells_per_frame, a.counts);           \
-    if (vec) reproject_offsets_kernel<T, true><<<g, kThreads, 0, stream>>>(a);                             \
-    else reproject_offsets_kernel<T, false><<<g, kThreads, 0, stream>>>(a);                                \
-  } while (0)
-      if (L.in_is_f32) D2PC_TWO_PASS(float);
-      else D2PC_TWO_PASS(uint8_t);
-#undef D2PC_TWO_PASS
-      if (launches) *launches += 3;
-      return cudaGetLastError();
-    }
-    if (a.d_sure_bits != 0 && L.in_is_f32 && vec && L.compact_variant == 5) {  // opt-in: measured slower than the band kernel
-      // pipeline kernel: R rows per tile, `stages` tiles resident per CTA; 8 consumer warps -> three CTAs per
-      // SM (~70 KB of stages each), 12 -> two CTAs per SM (~108 KB)
-      a.cw_pad = a.n_seg * kSegCols;
-      const size_t row_bytes = (size_t)a.cw_pad * sizeof(float);
-      const int consumers = L.pipe_consumers == 8 ? 8 : 12;
-      const int per_sm = consumers == 12 ? 2 : 3;
-      const size_t budget = (consumers == 12 ? 106 : 68) * 1024;
-      int stages = L.pipe_stages > 0 ? std::min(L.pipe_stages, kPipeMaxStages) : 6;
-      if (stages < 3) stages = 3;
-      while (stages > 3 && budget / (stages * row_bytes) < 1) --stages;
-      int r = (int)std::min<size_t>(budget / (stages * row_bytes), (size_t)kPipeMaxRows);
-      r = std::min(r, kPipeMaxUnits / a.n_seg);
-      if (L.rows_per_unit > 0) r = std::min(r, L.rows_per_unit);
-      if (r > (int)ch) r = (int)ch;
-      if (r >= 1) {
-        a.band_rows = r;
-        a.pipe_stages = stages;
-        a.pipe_consumers = consumers;
-        a.pipe_producers = (L.pipe_producers == 1 || L.pipe_producers == 2 || L.pipe_producers == 4) ? L.pipe_producers : 4;
-        if (consumers == 12 && a.pipe_producers == 1) a.pipe_producers = 2;
-        a.tiles_per_frame = (uint32_t)((ch + r - 1) / r);
-        const uint64_t total_t = (uint64_t)a.tiles_per_frame * L.n_frames;
-        if (total_t > 0xffffffffull) return cudaErrorInvalidValue;
-        grid = (int)std::min<uint64_t>(total_t, (uint64_t)L.sm_count * per_sm);
-      }
-    }
-    if (a.d_sure_bits != 0 && a.pipe_stages == 0 && (L.compact_variant == 0 || L.compact_variant == 3)) {
+    if (a.d_sure_bits != 0 && L.compact_variant != 1) {
       // band geometry: R rows per CTA (<= ~46 KB of disparities, <= 512 units), split into row groups so that
       // (segments x groups) fills the 8 warps evenly
       a.cw_pad = a.n_seg * kSegCols;
       const size_t row_bytes = (size_t)a.cw_pad * sizeof(float);
+      // four 8-warp CTAs of <= 46 KB per SM.  (Measured in round 2: eight 4-warp CTAs of <= 24 KB are slower, 0.79 vs
+      // 0.84 at 720p and 0.74 vs 0.90 at 4K, and so are smaller bands at 8 warps -- 4 rows: 0.65 -- the per-band
+      // fixed cost (ticket, row loads, scan, look-back) wants bands as large as the shared memory of 4 CTAs allows.)
+      const int bw = kCWarps;
       int r_max = (int)std::min<size_t>((46 * 1024) / row_bytes, (size_t)kBandMaxRows);
       r_max = std::min(r_max, kBandMaxUnits / a.n_seg);
       if (r_max < 1 && row_bytes <= 200 * 1024 && a.n_seg <= kBandMaxUnits) r_max = 1;
@@ -1849,7 +1076,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
         for (int g = 1; g <= r; ++g) {
           const int gr = (r + g - 1) / g, ga = (r + gr - 1) / gr;
           const int items = a.n_seg * ga;
-          const double eff = (double)items / (kCWarps * ((items + kCWarps - 1) / kCWarps));
+          const double eff = (double)items / (bw * ((items + bw - 1) / bw));
           const double score = eff * (gr / (gr + 0.6)) * (r / (r + 0.5));
           if (score > best + 1e-9) best = score, a.band_rows = r, a.band_groups = ga, a.group_rows = gr;
         }
@@ -1861,7 +1088,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
         a.prefetch_dist = L.prefetch_dist < 0 ? 0 : (L.prefetch_dist > 0 ? L.prefetch_dist : L.sm_count);  // measured plateau: 100-300 tiles
       }
     }
-    if (a.Q.rectified && !L.arith_fast && !L.force_generic && (a.band_rows == 0 || a.pipe_stages > 0)) {
+    if (a.Q.rectified && !L.arith_fast && !L.force_generic && a.band_rows == 0) {
       const int n = (int)(L.width + kSegCols > L.height ? L.width + kSegCols : L.height);
       rect_tables_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a.Q.q03, a.Q.q13, (int)L.width, (int)L.height, tabs,
                                                             tabs + L.width + kSegCols);

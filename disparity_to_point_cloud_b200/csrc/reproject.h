@@ -37,7 +37,6 @@ struct ReprojectLaunch {
   // compaction scratch (device): tile descriptors, ticket counter, launch epoch
   void *scratch = nullptr;
   void *tables = nullptr;      // reproject_table_bytes(width, height)
-  void *cells = nullptr;       // reproject_cells_bytes(...): two-pass CROP_FINITE cell counts / offsets
   uint32_t *ticket = nullptr;
   uint32_t epoch = 1;
   int sm_count = 148;
@@ -48,20 +47,14 @@ struct ReprojectLaunch {
   bool force_generic = false;  // exercise the generic-Q exact path on a rectified Q
   int exact_variant = 0;       // rectified exact quotients: 0 = guarded multiply (7 FP64 ops), 1 = Markstein (15)
   int compact_variant = 0;     // CROP_FINITE kernel: 0 = automatic (band where Q allows, else park),
-                               // 1 = park-then-compact, 2 = classify-first tiles, 3 = band, 5 = warp-specialised
-                               // TMA pipeline (1-3, 5: single pass, decoupled look-back),
-                               // 4 = two-pass count / scan / offset store (reads the disparity twice)
+                               // 1 = park-then-compact for every Q (test hook for the fallback)
   int prefetch_dist = 0;       // L2 prefetch distance: CROP kernel in work units, band kernel in tiles
                                // (0 = automatic, < 0 = off)
-  int pipe_stages = 0;         // pipeline kernel: stages per CTA (0 = automatic)
-  int pipe_producers = 0;      // pipeline kernel: producer warps per CTA (0 = automatic)
-  int pipe_consumers = 0;      // pipeline kernel: consumer warps per CTA (0 = automatic, 8 or 12)
 };
 
 void make_qparams(const double q[16], QParams *out);
 size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border);
 size_t reproject_table_bytes(uint32_t width, uint32_t height);
-size_t reproject_cells_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border);
 cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int *launches);
 
 }  // namespace d2pc

@@ -1,0 +1,196 @@
+#!/usr/bin/env python
+"""Development timings, one tool (none of it is product code, none of it imports the oracle):
+
+    python tools/timing.py crop [prefetch distances...]   headline CROP kernel vs L2 prefetch distance, 4K x16 / 720p x64
+    python tools/timing.py compact                        CROP_FINITE: band kernel vs the park fallback
+    python tools/timing.py generic                        rectified vs generic-Q exact arithmetic
+    python tools/timing.py median                         mono8 callback + median alone, per median variant / strip
+    python tools/timing.py score                          MatchingScoreCb1/2 (device entry)
+    python tools/timing.py latency                        synchronous per-call latency of the host entry points
+    python tools/timing.py stream                         end-to-end stream throughput vs pipeline depth
+
+Kernel timings use CUDA events on the context's compute stream after warm-up.
+"""
+import statistics
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import disparity_to_point_cloud_b200 as d2pc  # noqa: E402
+from disparity_to_point_cloud_b200 import synth  # noqa: E402
+
+PEAK = 6534.8  # GB/s, MEASURED_PEAKS.json on this pool
+
+
+def timer(ctx):
+    stream = torch.cuda.ExternalStream(ctx.compute_stream())
+
+    def t(fn, it=20, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(it):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / it * 1e-3
+    return t
+
+
+def float_batch(w, h, f, kind="s3"):
+    base = synth.s3_float(h, w, 3) if kind == "s3" else synth.s2_scene(h, w, 3).astype(np.float32) * np.float32(0.125)
+    base = torch.from_numpy(base).cuda()
+    return torch.stack([torch.roll(base, 17 * i, dims=1) for i in range(f)]).contiguous()
+
+
+def crop(argv):
+    ctx = d2pc.Context()
+    t = timer(ctx)
+    dists = [int(x) for x in argv] or [0, 256, 512, 1024, 2048]
+    for (w, h, f) in [(3840, 2160, 16), (1280, 720, 64)]:
+        n = (w - 80) * (h - 80)
+        d_in = float_batch(w, h, f)
+        d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
+        for dist in dists:
+            ctx.set_tuning("prefetch_dist", dist)
+            s = t(lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4, d_out.data_ptr(), n * 16), 30)
+            print(w, h, f, "prefetch", dist, "%.1f us  frac %.3f" % (s * 1e6, 20 * n * f / s / 1e9 / PEAK), flush=True)
+
+
+def compact(argv):
+    ctx = d2pc.Context()
+    t = timer(ctx)
+    for (w, h, f, kind) in [(1280, 720, 64, "s3"), (1280, 720, 64, "s2"), (3840, 2160, 16, "s3")]:
+        n = (w - 80) * (h - 80)
+        d_in = float_batch(w, h, f, kind)
+        d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(f, dtype=torch.int32, device="cuda")
+        ctx.set_filter_mode(1)
+        for variant, knobs in ((0, {}), (0, {"rows_per_unit": 4}), (0, {"ctas_per_sm": 3}), (1, {})):
+            ctx.set_tuning("compact_variant", variant)
+            for k, v in knobs.items():
+                ctx.set_tuning(k, v)
+            s = t(lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4, d_out.data_ptr(), n * 16,
+                                                   d_cnt.data_ptr()))
+            for k in knobs:
+                ctx.set_tuning(k, 0)
+            kept = int(d_cnt.sum().item())
+            by = 4 * n * f + 16 * kept
+            print(w, h, f, kind, "band" if variant == 0 else "park", knobs,
+                  "%.1f us  %.1f GB/s frac %.3f kept %.3f" % (s * 1e6, by / s / 1e9, by / s / 1e9 / PEAK, kept / (n * f)), flush=True)
+        ctx.set_tuning("compact_variant", 0)
+        ctx.set_filter_mode(0)
+
+
+def generic(argv):
+    ctx = d2pc.Context()
+    t = timer(ctx)
+    for (w, h, f) in [(3840, 2160, 16), (1280, 720, 64)]:
+        n = (w - 80) * (h - 80)
+        d_in = float_batch(w, h, f)
+        d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
+        for gen in (0, 1):
+            ctx.set_tuning("force_generic", gen)
+            s = t(lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4, d_out.data_ptr(), n * 16))
+            print(w, h, f, "generic" if gen else "rectified", "%.1f us  frac %.3f" % (s * 1e6, 20 * n * f / s / 1e9 / PEAK), flush=True)
+        ctx.set_tuning("force_generic", 0)
+
+
+def median(argv):
+    ctx = d2pc.Context()
+    t = timer(ctx)
+    variants = [int(x) for x in argv] or [0, 5, 3, 4]
+    for (w, h, f, kind) in [(752, 480, 256, "s2"), (752, 480, 256, "s1"), (3840, 2160, 8, "s2"), (752, 480, 1, "s2")]:
+        gen = synth.s2_scene if kind == "s2" else synth.s1_uniform
+        d = torch.from_numpy(np.stack([gen(h, w, i) for i in range(min(f, 8))])).cuda().repeat(max(1, f // 8), 1, 1)[:f].contiguous()
+        n = (w - 80) * (h - 80)
+        o = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
+        m = torch.empty_like(d)
+        for variant in variants:
+            ctx.set_tuning("median_variant", variant)
+            s_all = t(lambda: ctx.reproject_mono8_device(d.data_ptr(), f, w, h, w, w * h, o.data_ptr(), n * 16), 10, 3)
+            k = min(f, 4)
+            s_med = t(lambda: [ctx.median_u8_device(d[i].data_ptr(), w, h, w, m[i].data_ptr(), w, 11) for i in range(k)], 10, 3) / k
+            print(w, h, f, kind, "variant", variant, "callback: %.1f us/frame  %.1f Gpix/s | full-frame median alone: %.1f us/frame"
+                  % (s_all / f * 1e6, f * w * h / s_all / 1e9, s_med * 1e6), flush=True)
+        ctx.set_tuning("median_variant", 0)
+
+
+def score(argv):
+    ctx = d2pc.Context(offset_x=-7, offset_y=15)
+    t = timer(ctx)
+    for (w, h) in [(1280, 720), (752, 480)]:
+        s = torch.from_numpy(synth.s2_scene(h, w, 1)).cuda()
+        n = ctx.fuse_geometry(w, h)[4][0]
+        o = torch.empty((n, n), dtype=torch.uint8, device="cuda")
+        for which in (1, 2):
+            us = t(lambda: ctx.preprocess_score_device(s.data_ptr(), w, h, w, which, o.data_ptr()), 50) * 1e6
+            print(f"{w}x{h} MatchingScoreCb{which} (n = {n}): {us:.1f} us", flush=True)
+
+
+def latency(argv):
+    def lat(fn, n=200):
+        for _ in range(10):
+            fn()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return statistics.median(ts) * 1e6, ts[int(0.99 * n)] * 1e6
+
+    with d2pc.Context() as ctx:
+        for (w, h) in [(640, 480), (752, 480), (1280, 720)]:
+            img = synth.s2_scene(h, w, 1)
+            d = synth.s3_float(h, w, 1)
+            m8 = lat(lambda: ctx.process_mono8(img, copy=False))
+            f32 = lat(lambda: ctx.process_f32(d, copy=False))
+            # the message a subscriber publishes: library-owned cloud + the copy into the message (what pcl::toROSMsg
+            # does in the reference, cpp:84-85) versus the cloud DMA'd straight into a page-locked message buffer
+            n = (w - 80) * (h - 80) * 16
+            msg = np.empty(n, np.uint8)
+
+            def with_copy():
+                msg[:] = ctx.process_mono8(img, copy=False)
+
+            reg = d2pc.RegisteredArray(np.empty(n, np.uint8))
+            cp = lat(with_copy)
+            into = lat(lambda: ctx.process_into(img, reg.array))
+            reg.free()
+            print(f"{w}x{h}: process_mono8 median {m8[0]:.0f} us (p99 {m8[1]:.0f}), process_f32 median {f32[0]:.0f} us "
+                  f"(p99 {f32[1]:.0f}); mono8 -> message buffer: library cloud + memcpy {cp[0]:.0f} us (p99 {cp[1]:.0f}), "
+                  f"d2pc_process_mono8_into a registered buffer {into[0]:.0f} us (p99 {into[1]:.0f})", flush=True)
+
+
+def stream(argv):
+    for (w, h, dt, nfr) in [(752, 480, np.uint8, 2000), (3840, 2160, np.float32, 128), (1280, 720, np.float32, 1000)]:
+        pin = d2pc.PinnedArray((8, h, w), dt)
+        for i in range(8):
+            pin.array[i] = synth.s2_scene(h, w, 100 + i) if dt == np.uint8 else synth.s3_float(h, w, 100 + i)
+        for slots in (2, 3, 4, 6):
+            ctx = d2pc.Context(n_slots=slots)
+            ctx.process_stream(pin.array, collect=False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.process_stream(pin.array, collect=False, n_frames=nfr)
+            torch.cuda.synchronize()
+            s = time.perf_counter() - t0
+            n = (w - 80) * (h - 80)
+            print(f"{w}x{h} {np.dtype(dt).name} slots={slots}: {nfr/s:9.1f} frames/s  {nfr*w*h/s/1e6:9.1f} Mpix/s  "
+                  f"D2H {nfr*n*16/s/1e9:5.1f} GB/s  H2D {nfr*w*h*np.dtype(dt).itemsize/s/1e9:5.1f} GB/s", flush=True)
+            ctx.close()
+        pin.free()
+
+
+if __name__ == "__main__":
+    cmds = {"crop": crop, "compact": compact, "generic": generic, "median": median, "score": score, "latency": latency,
+            "stream": stream}
+    if len(sys.argv) < 2 or sys.argv[1] not in cmds:
+        raise SystemExit(__doc__)
+    cmds[sys.argv[1]](sys.argv[2:])
