@@ -17,7 +17,7 @@ struct MedianLaunch {
   int sm_count = 148;
   int strip_rows = 0;  // 0 = automatic
   int variant = 0;     // 0 = per-thread window histogram (Huang; a selection network for ksize 3),
-                       // 1 = column histograms, 2 = window histogram for every ksize
+                       // 2 = window histogram for every ksize (test hook)
 };
 
 cudaError_t launch_median_u8(const MedianLaunch &L, cudaStream_t stream, int *launches);

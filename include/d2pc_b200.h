@@ -321,7 +321,7 @@ size_t d2pc_serialize_pointcloud2(const d2pc_ctx *ctx, const d2pc_cloud *cloud, 
 /* Tuning / test hook: integer knobs by name.  Not needed in normal use.
  *   kernels : "rows_per_unit" (CROP: rows per work unit; band / pipeline kernels: rows per tile), "ctas_per_sm",
  *             "median_strip", "median_variant" (0 default: window histogram, 3x3 selection network; 2 window
- *             histogram for every size; 3 / 4 the SWAR-4 histogram experiments, atomics / load-store),
+ *             histogram for every size),
  *             "compact_variant" (0 auto: band kernel where Q allows; 1 park kernel for every Q),
  *             "prefetch_dist" (L2 prefetch distance in work units / tiles; 0 automatic, < 0 off),
  *             "exact_variant" (0 guarded multiply, 1 Markstein), "force_scalar", "force_generic"

@@ -7,14 +7,21 @@
  * only as the checker / the CPU baseline -- never on the product path.
  *
  * Parity pin: the reference has NO tests, fixtures or golden vectors
- * (CMakeLists.txt:206-217 has the gtest stanza commented out) and cannot be
- * compiled here (needs ROS1, cv_bridge, OpenCV C++ and PCL, none installed).
- * The arithmetic lives in un-vendored, un-pinned third-party libraries
- * (package.xml:41-55).  This oracle is therefore pinned against Python
- * cv2 4.13.0 (the same OpenCV entry points the reference calls, driven with
- * the reference's arguments): tests/golden/make_golden.py generates the
- * committed fixtures, tests/test_oracle_*.py replay them.  PCL / ROS message
- * semantics are restated from their public definitions (unpinned).
+ * (CMakeLists.txt:206-217 has the gtest stanza commented out) and its own build
+ * system cannot run here (needs ROS1, cv_bridge, OpenCV C++ and PCL, none
+ * installed).  This oracle is pinned two ways:
+ *   * third-party ARITHMETIC (un-vendored, un-pinned libraries, package.xml:41-55)
+ *     against Python cv2 4.13.0 -- the same OpenCV entry points the reference
+ *     calls, driven with the reference's arguments: tests/golden/make_golden.py
+ *     generates the committed fixtures, tests/test_oracle_*.py replay them;
+ *   * the reference's OWN LOGIC against the reference's own code: oracle/_ref is
+ *     src/depth_map_fusion.cpp + src/disparity_to_point_cloud.cpp compiled
+ *     unmodified against stand-in headers (oracle/ref_stubs/), and
+ *     tests/test_ref_compiled.py compares this file with it (gradFilter
+ *     exhaustively, the seven rules, the crop geometry, colorizeDepth, callback
+ *     sequences, DisparityCb's cloud).
+ * PCL's struct layout / toROSMsg, cv_bridge's copy and the ROS1 wire format
+ * are restated from their public definitions.
  *
  * All file:line citations are relative to /root/reference.
  */

@@ -104,7 +104,7 @@ def generic(argv):
 def median(argv):
     ctx = d2pc.Context()
     t = timer(ctx)
-    variants = [int(x) for x in argv] or [0, 5, 3, 4]
+    variants = [int(x) for x in argv] or [0, 2]
     for (w, h, f, kind) in [(752, 480, 256, "s2"), (752, 480, 256, "s1"), (3840, 2160, 8, "s2"), (752, 480, 1, "s2")]:
         gen = synth.s2_scene if kind == "s2" else synth.s1_uniform
         d = torch.from_numpy(np.stack([gen(h, w, i) for i in range(min(f, 8))])).cuda().repeat(max(1, f // 8), 1, 1)[:f].contiguous()
