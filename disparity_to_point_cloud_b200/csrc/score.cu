@@ -107,19 +107,34 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(const __grid_const
   if (a.submatrix) {
     // rows: R(fy, gc) over all F rows and the G columns; taps in order, FMA in the vector columns
     const int row_vec_end = n - n % 32, col_vec_end = n - n % 4;
-    for (int fy = warp; fy < kFW; fy += kWarps)
-      for (int gc = lane; gc < kGW; gc += 32) {
-        const int c = tx0 - kHG + gc;          // crop column (the tail rule only matters for 0 <= c < n)
-        const uint8_t *p = F + fy * kFP + gc;  // F column of crop column c - 6
-        const bool fma = c < row_vec_end;
-        float s = __fmul_rn(c_gauss13f[0], (float)p[0]);
+    // (a thread takes four adjacent output columns of one row: 16 pixels are loaded as four words and converted
+    // once, instead of 13 loads + 13 conversions per output; every output still runs its own tap sequence)
+    constexpr int kG4 = (kGW + 3) / 4;  // 23 groups of four columns
+    for (int item = (int)threadIdx.x; item < kFW * kG4; item += kThreads) {
+      const int fy = item / kG4, g = item - fy * kG4;
+      const uint32_t *pw = reinterpret_cast<const uint32_t *>(F + fy * kFP + 4 * g);  // F column of crop column c0 - 6
+      float v[16];
 #pragma unroll
-        for (int k = 1; k < 13; ++k) {
-          const float v = (float)p[k];
-          s = fma ? __fmaf_rn(c_gauss13f[k], v, s) : __fadd_rn(s, __fmul_rn(c_gauss13f[k], v));
-        }
-        R[fy * kGW + gc] = s;
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w = pw[j];
+        v[4 * j + 0] = (float)(w & 0xffu), v[4 * j + 1] = (float)((w >> 8) & 0xffu);
+        v[4 * j + 2] = (float)((w >> 16) & 0xffu), v[4 * j + 3] = (float)(w >> 24);
       }
+      const int c0 = tx0 - kHG + 4 * g;  // crop column of the first output (the tail rule only matters for 0 <= c < n)
+      float o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool fma = c0 + q < row_vec_end;
+        float acc = __fmul_rn(c_gauss13f[0], v[q]);
+#pragma unroll
+        for (int k = 1; k < 13; ++k)
+          acc = fma ? __fmaf_rn(c_gauss13f[k], v[q + k], acc) : __fadd_rn(acc, __fmul_rn(c_gauss13f[k], v[q + k]));
+        o[q] = acc;
+      }
+      float *dst = R + fy * kGW + 4 * g;
+      *reinterpret_cast<float2 *>(dst) = make_float2(o[0], o[1]);
+      if (4 * g + 2 < kGW) *reinterpret_cast<float2 *>(dst + 2) = make_float2(o[2], o[3]);
+    }
     __syncthreads();
     for (int gy = warp; gy < kGW; gy += kWarps) {
       const int ry = in_tile(reflect101(ty0 - kHG + gy, n), ty0, kHG);
@@ -218,29 +233,57 @@ __global__ void __launch_bounds__(kThreads) score_tile_kernel(const __grid_const
 
   // ---- second blur (fixed point) on E, then out = sat(score + 2 g)
   {
-    uint16_t *B = reinterpret_cast<uint16_t *>(R);  // [kEW][kT] 8.8
-    for (int ey = warp; ey < kEW; ey += kWarps)
-      for (int ox = lane; ox < kT; ox += 32) {
-        const int rx = in_tile(reflect101(tx0 + ox, n), tx0, 0);  // columns past the image edge are never stored
-        const uint8_t *p = E + ey * kEW + (rx - tx0);
+    // rows: four adjacent outputs per thread, the 21 taps as six 4-way byte dot products (DP4A) on the (shifted)
+    // words of E; the 8.8 row sums go into Bt TRANSPOSED ([column][row], pitch 86) so that the column pass finds its
+    // 21 vertical taps as consecutive 16-bit pairs and runs them as eleven 2-way dot products (DP2A).
+    constexpr int kBP = 86;  // u16 per Bt column: 84 rows + 2 (43 words: odd, so adjacent columns fall in different banks)
+    uint16_t *Bt = reinterpret_cast<uint16_t *>(R);  // [kT][kBP]
+    uint32_t k4[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      k4[j] = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (4 * j + b < 21) k4[j] |= (uint32_t)c_gauss21[4 * j + b] << (8 * b);
+    }
+    for (int item = (int)threadIdx.x; item < (kT / 4) * kEW; item += kThreads) {
+      const int g = item / kEW, ey = item - g * kEW;  // rows fastest: conflict-free loads (row pitch 21 words) and stores
+      const uint32_t *pw = reinterpret_cast<const uint32_t *>(E + ey * kEW + 4 * g);  // E column of output 4g, tap 0
+      uint32_t w[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) w[j] = pw[j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
         uint32_t acc = 0;
 #pragma unroll
-        for (int k = 0; k < 21; ++k) acc += (uint32_t)c_gauss21[k] * p[k];
-        B[ey * kT + ox] = (uint16_t)acc;
+        for (int j = 0; j < 6; ++j) {
+          const uint32_t sw = q == 0 ? w[j] : (j < 5 ? __funnelshift_r(w[j], w[j + 1], 8 * q) : (w[5] >> (8 * q)));
+          acc = __dp4a(sw, k4[j], acc);
+        }
+        Bt[(4 * g + q) * kBP + ey] = (uint16_t)acc;  // <= 255 * 256
       }
+    }
     __syncthreads();
+    // columns: output row oy needs Bt rows oy .. oy + 20; pairs are taken from the even row below oy, so the taps sit
+    // at pair offset p = oy & 1 and the weights are shifted to match (a zero weight on the unused half)
     for (int oy = warp; oy < kT; oy += kWarps) {
       const int y = ty0 + oy;
       if (y >= n) break;
+      const int par = oy & 1;
       for (int ox = lane; ox < kT; ox += 32) {
         const int x = tx0 + ox;
         if (x >= n) continue;
-        const uint16_t *t = B + oy * kT + ox;
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>(Bt + ox * kBP + (oy - par));
         uint32_t acc = 0;
 #pragma unroll
-        for (int k = 0; k < 21; ++k) acc += (uint32_t)c_gauss21[k] * t[k * kT];
-        const uint32_t g = min((acc + 32768u) >> 16, 255u);
-        a.out[(size_t)y * n + x] = (uint8_t)min((uint32_t)S[oy * kT + ox] + 2u * g, 255u);
+        for (int j = 0; j < 11; ++j) {
+          const int i0 = 2 * j - par, i1 = i0 + 1;  // taps of the two halves of word j
+          const uint32_t wlo = (i0 >= 0 && i0 < 21) ? (uint32_t)c_gauss21[i0] : 0u;
+          const uint32_t whi = (i1 >= 0 && i1 < 21) ? (uint32_t)c_gauss21[i1] : 0u;
+          acc = __dp2a_lo(pw[j], wlo | (whi << 8), acc);
+        }
+        const uint32_t gq = min((acc + 32768u) >> 16, 255u);
+        a.out[(size_t)y * n + x] = (uint8_t)min((uint32_t)S[oy * kT + ox] + 2u * gq, 255u);
       }
     }
   }
