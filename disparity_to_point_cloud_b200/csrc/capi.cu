@@ -350,8 +350,10 @@ int slot_wait_idle(d2pc_ctx *ctx, Slot &s) {
   return D2PC_OK;
 }
 
+// serial: the synchronous single-frame entries (d2pc_process_*) have nothing to overlap with, so they enqueue the
+// copy in, the kernels and the copy out on ONE stream: no cross-stream event hand-offs on the latency path.
 int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_t h, uint32_t step, bool is_f32,
-                  uint8_t *user_dst = nullptr, size_t user_cap = 0) {
+                  uint8_t *user_dst = nullptr, size_t user_cap = 0, bool serial = false) {
   if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return D2PC_ERR_INVALID_ARG;
   const int esz = is_f32 ? 4 : 1;
   int rc = check_frame(ctx, data, w, h, step, esz);
@@ -391,29 +393,32 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
     src = s.h_in.p;
     src_pitch = row_bytes;
   }
+  cudaStream_t st_in = serial ? ctx->s_compute : ctx->s_h2d, st_out = serial ? ctx->s_compute : ctx->s_d2h;
   if (src_pitch == row_bytes && d_pitch == row_bytes)
-    CU(ctx, cudaMemcpyAsync(s.d_in.p, src, row_bytes * h, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(ctx, cudaMemcpyAsync(s.d_in.p, src, row_bytes * h, cudaMemcpyHostToDevice, st_in));
   else
-    CU(ctx, cudaMemcpy2DAsync(s.d_in.p, d_pitch, src, src_pitch, row_bytes, h, cudaMemcpyHostToDevice, ctx->s_h2d));
-  CU(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
-
-  // ---- kernels (stream 2)
-  CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
+    CU(ctx, cudaMemcpy2DAsync(s.d_in.p, d_pitch, src, src_pitch, row_bytes, h, cudaMemcpyHostToDevice, st_in));
+  if (!serial) {
+    CU(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
+    // ---- kernels (stream 2)
+    CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
+  }
   rc = enqueue_kernels(ctx, s.d_in.p, is_f32, 1, w, h, d_pitch, d_pitch * h, s.d_med.p, s.d_out.p, n * 16 + 16,
                        s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
   if (rc) return rc;
-  CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
-
-  // ---- D2H (stream 3)
-  CU(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_kernel, 0));
+  if (!serial) {
+    CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
+    // ---- D2H (stream 3)
+    CU(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_kernel, 0));
+  }
   if (compact) {
     // the kept count decides how many bytes travel: fetch it, the payload copy is issued in d2pc_wait
-    CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_out));
   } else if (n) {
     // a page-locked caller buffer receives the cloud by DMA directly; a pageable one is filled from h_out in wait
-    CU(ctx, cudaMemcpyAsync(user_pinned ? user_dst : s.h_out.p, s.d_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU(ctx, cudaMemcpyAsync(user_pinned ? user_dst : s.h_out.p, s.d_out.p, n * 16, cudaMemcpyDeviceToHost, st_out));
   }
-  CU(ctx, cudaEventRecord(s.ev_d2h, ctx->s_d2h));
+  CU(ctx, cudaEventRecord(s.ev_d2h, st_out));
   s.pending = true;
   s.width = w;
   s.height = h;
@@ -711,23 +716,25 @@ int d2pc_submit_f32_into(d2pc_ctx *ctx, int slot, const float *disp, uint32_t w,
 }
 int d2pc_process_mono8_into(d2pc_ctx *ctx, const uint8_t *data, uint32_t w, uint32_t h, uint32_t step, uint8_t *dst,
                             size_t cap, d2pc_cloud *out) {
-  int rc = d2pc_submit_mono8_into(ctx, 0, data, w, h, step, dst, cap);
+  if (!dst) return D2PC_ERR_INVALID_ARG;
+  int rc = submit_common(ctx, 0, data, w, h, step, false, dst, cap, /*serial=*/true);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 int d2pc_process_f32_into(d2pc_ctx *ctx, const float *disp, uint32_t w, uint32_t h, uint32_t step, uint8_t *dst,
                           size_t cap, d2pc_cloud *out) {
-  int rc = d2pc_submit_f32_into(ctx, 0, disp, w, h, step, dst, cap);
+  if (!dst) return D2PC_ERR_INVALID_ARG;
+  int rc = submit_common(ctx, 0, disp, w, h, step, true, dst, cap, /*serial=*/true);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 
 int d2pc_process_mono8(d2pc_ctx *ctx, const uint8_t *data, uint32_t w, uint32_t h, uint32_t step, d2pc_cloud *out) {
   if (!out) return D2PC_ERR_INVALID_ARG;
-  int rc = d2pc_submit_mono8(ctx, 0, data, w, h, step);
+  int rc = submit_common(ctx, 0, data, w, h, step, false, nullptr, 0, /*serial=*/true);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 int d2pc_process_f32(d2pc_ctx *ctx, const float *disp, uint32_t w, uint32_t h, uint32_t step, d2pc_cloud *out) {
   if (!out) return D2PC_ERR_INVALID_ARG;
-  int rc = d2pc_submit_f32(ctx, 0, disp, w, h, step);
+  int rc = submit_common(ctx, 0, disp, w, h, step, true, nullptr, 0, /*serial=*/true);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 
