@@ -54,6 +54,7 @@ struct Slot {
   uint32_t *d_count = nullptr;  // [0] = kept points, [1] = compaction ticket
   uint32_t *h_count = nullptr;  // pinned
   cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr;
+  cudaStream_t s_kern = nullptr;  // fusion pipeline: this slot's own kernel stream (small kernels of consecutive sets overlap)
   bool pending = false;
   uint32_t width = 0, height = 0;
   uint64_t n_points = 0;
@@ -350,10 +351,8 @@ int slot_wait_idle(d2pc_ctx *ctx, Slot &s) {
   return D2PC_OK;
 }
 
-// serial: the synchronous single-frame entries (d2pc_process_*) have nothing to overlap with, so they enqueue the
-// copy in, the kernels and the copy out on ONE stream: no cross-stream event hand-offs on the latency path.
 int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_t h, uint32_t step, bool is_f32,
-                  uint8_t *user_dst = nullptr, size_t user_cap = 0, bool serial = false) {
+                  uint8_t *user_dst = nullptr, size_t user_cap = 0) {
   if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return D2PC_ERR_INVALID_ARG;
   const int esz = is_f32 ? 4 : 1;
   int rc = check_frame(ctx, data, w, h, step, esz);
@@ -393,32 +392,29 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
     src = s.h_in.p;
     src_pitch = row_bytes;
   }
-  cudaStream_t st_in = serial ? ctx->s_compute : ctx->s_h2d, st_out = serial ? ctx->s_compute : ctx->s_d2h;
   if (src_pitch == row_bytes && d_pitch == row_bytes)
-    CU(ctx, cudaMemcpyAsync(s.d_in.p, src, row_bytes * h, cudaMemcpyHostToDevice, st_in));
+    CU(ctx, cudaMemcpyAsync(s.d_in.p, src, row_bytes * h, cudaMemcpyHostToDevice, ctx->s_h2d));
   else
-    CU(ctx, cudaMemcpy2DAsync(s.d_in.p, d_pitch, src, src_pitch, row_bytes, h, cudaMemcpyHostToDevice, st_in));
-  if (!serial) {
-    CU(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
-    // ---- kernels (stream 2)
-    CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
-  }
+    CU(ctx, cudaMemcpy2DAsync(s.d_in.p, d_pitch, src, src_pitch, row_bytes, h, cudaMemcpyHostToDevice, ctx->s_h2d));
+  CU(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
+
+  // ---- kernels (stream 2)
+  CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
   rc = enqueue_kernels(ctx, s.d_in.p, is_f32, 1, w, h, d_pitch, d_pitch * h, s.d_med.p, s.d_out.p, n * 16 + 16,
                        s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
   if (rc) return rc;
-  if (!serial) {
-    CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
-    // ---- D2H (stream 3)
-    CU(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_kernel, 0));
-  }
+  CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
+
+  // ---- D2H (stream 3)
+  CU(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_kernel, 0));
   if (compact) {
     // the kept count decides how many bytes travel: fetch it, the payload copy is issued in d2pc_wait
-    CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_out));
+    CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
   } else if (n) {
     // a page-locked caller buffer receives the cloud by DMA directly; a pageable one is filled from h_out in wait
-    CU(ctx, cudaMemcpyAsync(user_pinned ? user_dst : s.h_out.p, s.d_out.p, n * 16, cudaMemcpyDeviceToHost, st_out));
+    CU(ctx, cudaMemcpyAsync(user_pinned ? user_dst : s.h_out.p, s.d_out.p, n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
   }
-  CU(ctx, cudaEventRecord(s.ev_d2h, st_out));
+  CU(ctx, cudaEventRecord(s.ev_d2h, ctx->s_d2h));
   s.pending = true;
   s.width = w;
   s.height = h;
@@ -552,7 +548,8 @@ int d2pc_create(const d2pc_config *cfg, int device, d2pc_ctx **out) {
   for (auto &s : ctx->slots) {
     if (cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.ev_kernel, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s.s_kern, cudaStreamNonBlocking) != cudaSuccess)
       return fail(D2PC_ERR_CUDA);
     if (cudaMalloc(&s.d_count, 64) != cudaSuccess) return fail(D2PC_ERR_NOMEM);
     if (cudaHostAlloc(&s.h_count, 64, cudaHostAllocDefault) != cudaSuccess) return fail(D2PC_ERR_NOMEM);
@@ -596,6 +593,7 @@ void d2pc_destroy(d2pc_ctx *ctx) {
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
     if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    if (s.s_kern) cudaStreamDestroy(s.s_kern);
   }
   free_dev(ctx->d_scratch), free_dev(ctx->d_tables), free_dev(ctx->d_med_batch);
   for (auto &b : ctx->d_fuse_in) free_dev(b);
@@ -716,25 +714,23 @@ int d2pc_submit_f32_into(d2pc_ctx *ctx, int slot, const float *disp, uint32_t w,
 }
 int d2pc_process_mono8_into(d2pc_ctx *ctx, const uint8_t *data, uint32_t w, uint32_t h, uint32_t step, uint8_t *dst,
                             size_t cap, d2pc_cloud *out) {
-  if (!dst) return D2PC_ERR_INVALID_ARG;
-  int rc = submit_common(ctx, 0, data, w, h, step, false, dst, cap, /*serial=*/true);
+  int rc = d2pc_submit_mono8_into(ctx, 0, data, w, h, step, dst, cap);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 int d2pc_process_f32_into(d2pc_ctx *ctx, const float *disp, uint32_t w, uint32_t h, uint32_t step, uint8_t *dst,
                           size_t cap, d2pc_cloud *out) {
-  if (!dst) return D2PC_ERR_INVALID_ARG;
-  int rc = submit_common(ctx, 0, disp, w, h, step, true, dst, cap, /*serial=*/true);
+  int rc = d2pc_submit_f32_into(ctx, 0, disp, w, h, step, dst, cap);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 
 int d2pc_process_mono8(d2pc_ctx *ctx, const uint8_t *data, uint32_t w, uint32_t h, uint32_t step, d2pc_cloud *out) {
   if (!out) return D2PC_ERR_INVALID_ARG;
-  int rc = submit_common(ctx, 0, data, w, h, step, false, nullptr, 0, /*serial=*/true);
+  int rc = d2pc_submit_mono8(ctx, 0, data, w, h, step);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 int d2pc_process_f32(d2pc_ctx *ctx, const float *disp, uint32_t w, uint32_t h, uint32_t step, d2pc_cloud *out) {
   if (!out) return D2PC_ERR_INVALID_ARG;
-  int rc = submit_common(ctx, 0, disp, w, h, step, true, nullptr, 0, /*serial=*/true);
+  int rc = d2pc_submit_f32(ctx, 0, disp, w, h, step);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 
@@ -879,6 +875,8 @@ int d2pc_sync(d2pc_ctx *ctx) {
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->s_h2d));
   CU(ctx, cudaStreamSynchronize(ctx->s_compute));
+  for (auto &s : ctx->slots)
+    if (s.s_kern) CU(ctx, cudaStreamSynchronize(s.s_kern));
   CU(ctx, cudaStreamSynchronize(ctx->s_d2h));
   return D2PC_OK;
 }
@@ -903,7 +901,9 @@ int d2pc_fuse_geometry(const d2pc_ctx *ctx, uint32_t w, uint32_t h, int rect1[4]
 
 static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t *s1, const uint8_t *s2,
                             uint32_t w, uint32_t h, size_t step, uint8_t *d_fused, uint8_t *d_combined,
-                            FuseGeometry *g_out, bool scores_cropped = false, DevBuf *container = nullptr) {
+                            FuseGeometry *g_out, bool scores_cropped = false, DevBuf *container = nullptr,
+                            cudaStream_t stream = nullptr) {
+  if (!stream) stream = ctx->s_compute;
   const d2pc_config &c = ctx->cfg;
   FuseGeometry g;
   if (!fuse_geometry((int)w, (int)h, c.offset_x, c.offset_y, c.fuse_crop_left, c.fuse_crop_right, c.fuse_crop_top,
@@ -925,7 +925,7 @@ static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2,
   L.container = cont.p;
   L.combined = d_combined;
   int nl = 0;
-  CU(ctx, launch_fuse_merge(L, ctx->s_compute, &nl));
+  CU(ctx, launch_fuse_merge(L, stream, &nl));
   ctx->launches += nl;
   if (c.fuse_median_ksize > 1) {
     // :124 medianBlur on the container ROI (its edge is the replicate border), then :130 cropMat -- produced as
@@ -941,11 +941,11 @@ static int fuse_device_impl(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2,
     M.ksize = c.fuse_median_ksize;
     M.sm_count = ctx->sm_count;
     M.variant = ctx->median_variant;
-    CU(ctx, launch_median_u8(M, ctx->s_compute, &nl));
+    CU(ctx, launch_median_u8(M, stream, &nl));
     ctx->launches += nl;
   } else {
     CU(ctx, cudaMemcpy2DAsync(d_fused, g.out_w, cont.p + (size_t)g.out_y * g.nc + g.out_x, g.nc, g.out_w,
-                              g.out_h, cudaMemcpyDeviceToDevice, ctx->s_compute));
+                              g.out_h, cudaMemcpyDeviceToDevice, stream));
   }
   if (g_out) *g_out = g;
   return D2PC_OK;
@@ -1013,7 +1013,8 @@ int d2pc_fuse(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, const uint8_t
 
 // ---- matching-score preprocessing -----------------------------------------------------------------------
 static int score_device_impl(d2pc_ctx *ctx, const uint8_t *d_score, uint32_t w, uint32_t h, size_t step, int which,
-                             uint8_t *d_out, int *n_out) {
+                             uint8_t *d_out, int *n_out, cudaStream_t stream = nullptr) {
+  if (!stream) stream = ctx->s_compute;
   const d2pc_config &c = ctx->cfg;
   FuseGeometry g;
   fuse_geometry((int)w, (int)h, c.offset_x, c.offset_y, c.fuse_crop_left, c.fuse_crop_right, c.fuse_crop_top,
@@ -1034,7 +1035,7 @@ static int score_device_impl(d2pc_ctx *ctx, const uint8_t *d_score, uint32_t w, 
   for (int i = 0; i < 4; ++i) L.rect[i] = r[i];
   L.out = d_out;
   int nl = 0;
-  CU(ctx, launch_score_preprocess(L, ctx->s_compute, &nl));
+  CU(ctx, launch_score_preprocess(L, stream, &nl));
   ctx->launches += nl;
   if (n_out) *n_out = n;
   return D2PC_OK;
@@ -1218,22 +1219,25 @@ int d2pc_submit_fusion(d2pc_ctx *ctx, int slot, const uint8_t *d1, const uint8_t
   }
   CU(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
 
-  // ---- kernels (stream 2): MatchingScoreCb1/2 -> merge -> median 3 + trim -> DisparityCb on the fused map
-  CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
+  // ---- kernels: MatchingScoreCb1/2 -> merge -> median 3 + trim -> DisparityCb on the fused map.  Six small
+  // kernels (~100 us together, none of which fills the chip): each slot launches them on its own stream, so the
+  // sets of consecutive slots overlap on the GPU instead of queueing behind each other.
+  cudaStream_t sk = s.s_kern;
+  CU(ctx, cudaStreamWaitEvent(sk, s.ev_h2d, 0));
   const uint8_t *sc1 = s.d_fuse_in[2].p, *sc2 = s.d_fuse_in[3].p;
   if (preprocess_scores) {
-    if ((rc = score_device_impl(ctx, s.d_fuse_in[2].p, w, h, pitch, 1, s.d_pre[0].p, nullptr)) ||
-        (rc = score_device_impl(ctx, s.d_fuse_in[3].p, w, h, pitch, 2, s.d_pre[1].p, nullptr)))
+    if ((rc = score_device_impl(ctx, s.d_fuse_in[2].p, w, h, pitch, 1, s.d_pre[0].p, nullptr, sk)) ||
+        (rc = score_device_impl(ctx, s.d_fuse_in[3].p, w, h, pitch, 2, s.d_pre[1].p, nullptr, sk)))
       return rc;
     sc1 = s.d_pre[0].p, sc2 = s.d_pre[1].p;
   }
   if ((rc = fuse_device_impl(ctx, s.d_fuse_in[0].p, s.d_fuse_in[1].p, sc1, sc2, w, h, pitch, s.d_fused.p, s.d_combined.p,
-                             nullptr, preprocess_scores != 0, &s.d_container)))
+                             nullptr, preprocess_scores != 0, &s.d_container, sk)))
     return rc;
   rc = enqueue_kernels(ctx, s.d_fused.p, false, 1, fw, fh, fw, (size_t)fw * fh, s.d_med.p, s.d_out.p, n * 16 + 16, s.d_count,
-                       s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
+                       s.d_scratch.p, s.d_tables.p, s.d_count + 1, sk);
   if (rc) return rc;
-  CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
+  CU(ctx, cudaEventRecord(s.ev_kernel, sk));
 
   // ---- D2H (stream 3)
   CU(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_kernel, 0));

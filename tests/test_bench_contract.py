@@ -33,3 +33,24 @@ def test_product_arm_refuses_to_run_without_a_gpu():
                          timeout=600, cwd=ROOT)
     assert out.returncode != 0
     assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_algorithmic_bytes_are_the_survey_figures():
+    """20 N bytes per float frame (15.36 MB at 1280x720, 156.416 MB at 3840x2160), (W-70)(H-70) + 16 N
+    for the mono8 callback; both arms describe a config with the same workload string."""
+    import bench
+    assert bench.algorithmic_bytes(bench.CONFIGS[3]) == 15_360_000
+    assert bench.algorithmic_bytes(bench.CONFIGS[4]) == 156_416_000
+    assert bench.algorithmic_bytes(bench.CONFIGS[2]) == (752 - 70) * (480 - 70) + 16 * 268_800
+    assert bench.fusion_dims(1280, 720) == (705, 665, 665)
+    assert bench.unit_pixels(bench.CONFIGS[5]) == 4 * 1280 * 720
+    assert len({c["workload"] for c in bench.CONFIGS.values()}) == 4
+
+
+def test_reference_arm_other_configs_share_the_workload_string():
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "3", "--steps", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["config"]["workload"] == bench.CONFIGS[3]["workload"] and d["cpu_baseline"]["kind"] == "port"
