@@ -62,6 +62,11 @@ class Cloud(C.Structure):
         return np.ctypeslib.as_array(self.data, shape=(n,))
 
 
+class Timing(C.Structure):
+    _fields_ = [("h2d_us", C.c_float), ("kernels_us", C.c_float), ("d2h_us", C.c_float), ("total_us", C.c_float),
+                ("points", C.c_uint64)]
+
+
 class Image(C.Structure):
     _fields_ = [("data", C.POINTER(C.c_uint8)), ("width", C.c_uint32), ("height", C.c_uint32), ("step", C.c_uint32)]
 
@@ -97,6 +102,8 @@ SYMBOLS = [
                                           C.POINTER(Cloud)]),
     ("d2pc_process_f32_into", C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
                                         C.POINTER(Cloud)]),
+    ("d2pc_set_timing", C.c_int, [_ctx, C.c_int]),
+    ("d2pc_slot_timing", C.c_int, [_ctx, C.c_int, C.POINTER(Timing)]),
     ("d2pc_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     ("d2pc_host_free", C.c_int, [C.c_void_p]),
     ("d2pc_host_register", C.c_int, [C.c_void_p, C.c_size_t]),
@@ -280,6 +287,14 @@ class Context:
 
     def set_arith_mode(self, m):
         self._check(lib().d2pc_set_arith_mode(self._h, m), "d2pc_set_arith_mode")
+
+    def set_timing(self, enable: bool = True):
+        self._check(lib().d2pc_set_timing(self._h, 1 if enable else 0), "d2pc_set_timing")
+
+    def slot_timing(self, slot: int = 0) -> Timing:
+        t = Timing()
+        self._check(lib().d2pc_slot_timing(self._h, slot, C.byref(t)), "d2pc_slot_timing")
+        return t
 
     def set_tuning(self, key: str, value: int):
         self._check(lib().d2pc_set_tuning(self._h, key.encode(), int(value)), f"d2pc_set_tuning({key})")

@@ -23,6 +23,7 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
 #include <sys/mman.h>
 
 #include "fusion.h"
@@ -54,6 +55,8 @@ struct Slot {
   uint32_t *d_count = nullptr;  // [0] = kept points, [1] = compaction ticket
   uint32_t *h_count = nullptr;  // pinned
   cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr;
+  cudaEvent_t ev_start = nullptr;  // recorded in front of the H2D copy when per-call timing is on (d2pc_set_timing)
+  bool timed = false;              // the last submission on this slot recorded all four events with timing
   cudaStream_t s_kern = nullptr;  // fusion pipeline: this slot's own kernel stream (small kernels of consecutive sets overlap)
   bool pending = false;
   uint32_t width = 0, height = 0;
@@ -94,11 +97,19 @@ struct d2pc_ctx {
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0, median_variant = 0;
   bool force_scalar = false, force_generic = false;
   int compact_variant = 0, exact_variant = 0, prefetch_dist = 0;
+  bool timing = false;  // d2pc_set_timing: slot events carry timestamps
   std::vector<std::pair<uintptr_t, bool>> pin_cache;  // host pointer -> pinned (cudaHostAlloc / cudaHostRegister)?
   uint64_t pin_cache_gen = 0;                         // value of g_host_gen the cache was filled under
 };
 
 namespace {
+
+// NVTX range for the host-side span of an entry point (ranges around H2D / kernels / D2H);
+// free when no profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // bumped whenever pinned host memory is released (d2pc_host_free / d2pc_host_unregister): a context's
 // pointer -> "is pinned" cache is only trusted while this has not moved, so a freed and re-allocated address is
@@ -361,6 +372,7 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   Slot &s = ctx->slots[slot];
   rc = slot_wait_idle(ctx, s);
   if (rc) return rc;
+  NvtxRange nvtx_submit(is_f32 ? "d2pc submit f32" : "d2pc submit mono8");
 
   const size_t row_bytes = (size_t)w * esz;
   // rows that are already 16-byte multiples stay dense on the device: the H2D copy is then one contiguous DMA
@@ -392,20 +404,29 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
     src = s.h_in.p;
     src_pitch = row_bytes;
   }
-  if (src_pitch == row_bytes && d_pitch == row_bytes)
-    CU(ctx, cudaMemcpyAsync(s.d_in.p, src, row_bytes * h, cudaMemcpyHostToDevice, ctx->s_h2d));
-  else
-    CU(ctx, cudaMemcpy2DAsync(s.d_in.p, d_pitch, src, src_pitch, row_bytes, h, cudaMemcpyHostToDevice, ctx->s_h2d));
-  CU(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
+  s.timed = ctx->timing && s.ev_start;
+  if (s.timed) CU(ctx, cudaEventRecord(s.ev_start, ctx->s_h2d));
+  {
+    NvtxRange nvtx_h2d("d2pc H2D");
+    if (src_pitch == row_bytes && d_pitch == row_bytes)
+      CU(ctx, cudaMemcpyAsync(s.d_in.p, src, row_bytes * h, cudaMemcpyHostToDevice, ctx->s_h2d));
+    else
+      CU(ctx, cudaMemcpy2DAsync(s.d_in.p, d_pitch, src, src_pitch, row_bytes, h, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
+  }
 
   // ---- kernels (stream 2)
   CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
-  rc = enqueue_kernels(ctx, s.d_in.p, is_f32, 1, w, h, d_pitch, d_pitch * h, s.d_med.p, s.d_out.p, n * 16 + 16,
-                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
+  {
+    NvtxRange nvtx_k("d2pc kernels");
+    rc = enqueue_kernels(ctx, s.d_in.p, is_f32, 1, w, h, d_pitch, d_pitch * h, s.d_med.p, s.d_out.p, n * 16 + 16,
+                         s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
+  }
   if (rc) return rc;
   CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
 
   // ---- D2H (stream 3)
+  NvtxRange nvtx_d2h("d2pc D2H");
   CU(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_kernel, 0));
   if (compact) {
     // the kept count decides how many bytes travel: fetch it, the payload copy is issued in d2pc_wait
@@ -593,6 +614,7 @@ void d2pc_destroy(d2pc_ctx *ctx) {
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
     if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.s_kern) cudaStreamDestroy(s.s_kern);
   }
   free_dev(ctx->d_scratch), free_dev(ctx->d_tables), free_dev(ctx->d_med_batch);
@@ -732,6 +754,41 @@ int d2pc_process_f32(d2pc_ctx *ctx, const float *disp, uint32_t w, uint32_t h, u
   if (!out) return D2PC_ERR_INVALID_ARG;
   int rc = d2pc_submit_f32(ctx, 0, disp, w, h, step);
   return rc ? rc : d2pc_wait(ctx, 0, out);
+}
+
+// ---- per-call timing ("per-call timing struct returned through the C ABI") ---------------
+int d2pc_set_timing(d2pc_ctx *ctx, int enable) {
+  if (!ctx) return D2PC_ERR_INVALID_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaDeviceSynchronize());  // no slot may be in flight while its events are replaced
+  const unsigned flags = enable ? cudaEventDefault : cudaEventDisableTiming;
+  for (auto &s : ctx->slots) {
+    s.pending = false;
+    s.timed = false;
+    cudaEvent_t *evs[4] = {&s.ev_start, &s.ev_h2d, &s.ev_kernel, &s.ev_d2h};
+    for (cudaEvent_t *e : evs) {
+      if (*e) CU(ctx, cudaEventDestroy(*e));
+      *e = nullptr;
+      CU(ctx, cudaEventCreateWithFlags(e, flags));
+    }
+  }
+  ctx->timing = enable != 0;
+  return D2PC_OK;
+}
+
+int d2pc_slot_timing(d2pc_ctx *ctx, int slot, d2pc_timing *out) {
+  if (!ctx || !out || slot < 0 || slot >= (int)ctx->slots.size()) return D2PC_ERR_INVALID_ARG;
+  Slot &s = ctx->slots[slot];
+  if (!ctx->timing || !s.timed || s.pending) return D2PC_ERR_NOT_READY;  // enable timing, submit, wait, then ask
+  CU(ctx, cudaSetDevice(ctx->device));
+  float h2d = 0.f, ker = 0.f, d2h = 0.f, tot = 0.f;
+  CU(ctx, cudaEventElapsedTime(&h2d, s.ev_start, s.ev_h2d));
+  CU(ctx, cudaEventElapsedTime(&ker, s.ev_h2d, s.ev_kernel));
+  CU(ctx, cudaEventElapsedTime(&d2h, s.ev_kernel, s.ev_d2h));
+  CU(ctx, cudaEventElapsedTime(&tot, s.ev_start, s.ev_d2h));
+  out->h2d_us = h2d * 1e3f, out->kernels_us = ker * 1e3f, out->d2h_us = d2h * 1e3f, out->total_us = tot * 1e3f;
+  out->points = s.compact ? (s.n_points ? s.h_count[0] : 0) : s.n_points;
+  return D2PC_OK;
 }
 
 int d2pc_host_alloc(void **ptr, size_t bytes) {
@@ -1202,6 +1259,9 @@ int d2pc_submit_fusion(d2pc_ctx *ctx, int slot, const uint8_t *d1, const uint8_t
                   (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(fw, fh)))))
     return rc;
 
+  NvtxRange nvtx_submit("d2pc submit fusion set");
+  s.timed = ctx->timing && s.ev_start;
+  if (s.timed) CU(ctx, cudaEventRecord(s.ev_start, ctx->s_h2d));
   // ---- H2D (stream 1): pinned caller frames are DMA'd in place, pageable ones are staged
   const uint8_t *in[4] = {d1, d2, s1, s2};
   for (int i = 0; i < 4; ++i) {

@@ -188,6 +188,20 @@ int d2pc_process_mono8_into(d2pc_ctx *ctx, const uint8_t *data, uint32_t width, 
 int d2pc_process_f32_into(d2pc_ctx *ctx, const float *disp, uint32_t width, uint32_t height, uint32_t step,
                           uint8_t *dst, size_t cap, d2pc_cloud *out);
 
+/* Per-call timing (the reference's only instrumentation is nine printf lines per frame,
+ * src/disparity_to_point_cloud.cpp:47-91).  d2pc_set_timing(ctx, 1) makes the slots' events carry timestamps
+ * (waits for the device; call it between frames); after d2pc_wait(slot) d2pc_slot_timing reports where that
+ * submission's time went on the device: the spans between the events that chain H2D copy -> kernels -> D2H copy
+ * (queueing behind other slots included).  In CROP_FINITE mode d2h_us covers the 4-byte count only (the payload
+ * is copied inside d2pc_wait).  The host-side spans of every entry point are also NVTX ranges ("d2pc submit ...",
+ * "d2pc H2D", "d2pc kernels", "d2pc D2H") for Nsight. */
+typedef struct d2pc_timing {
+  float h2d_us, kernels_us, d2h_us, total_us;
+  uint64_t points; /* points of that cloud */
+} d2pc_timing;
+int d2pc_set_timing(d2pc_ctx *ctx, int enable);
+int d2pc_slot_timing(d2pc_ctx *ctx, int slot, d2pc_timing *out);
+
 /* Pinned host memory for buffers the caller wants DMA'd without staging: allocate it here, or page-lock memory
  * the caller already owns (cudaHostRegister; costs about as much as touching every page once, so register
  * long-lived buffers, not one per message). */

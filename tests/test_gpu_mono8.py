@@ -192,6 +192,35 @@ def test_caller_supplied_destination(ctx, q):
         reg.free()
 
 
+def test_per_call_timing(q):
+    """d2pc_set_timing / d2pc_slot_timing: the device-side spans of one submission (H2D, kernels, D2H) are positive,
+    add up to the total, and the call still produces the same bytes; without timing enabled the query says so."""
+    import disparity_to_point_cloud_b200 as d2pc
+    img = synth.s2_scene(480, 752, 33)
+    want = oracle.disparity_cb_mono8(img, q)
+    with d2pc.Context() as c:
+        c.process_mono8(img)
+        with pytest.raises(d2pc.D2pcError) as e:
+            c.slot_timing(0)
+        assert e.value.status == -8
+        c.set_timing(True)
+        for _ in range(3):
+            assert_same_bits(c.process_mono8(img), want, "timed call")
+        t = c.slot_timing(0)
+        assert t.points == want.size // 16
+        assert t.h2d_us > 0 and t.kernels_us > 5 and t.d2h_us > 20 and t.total_us < 5000
+        assert abs(t.h2d_us + t.kernels_us + t.d2h_us - t.total_us) < 0.05 * t.total_us + 2
+        c.submit(1, img)
+        c.wait(1)
+        assert c.slot_timing(1).kernels_us > 5
+        four = [synth.s2_scene(240, 320, 2 + i) for i in range(4)]
+        c.submit_fusion(2, *four)
+        c.wait(2)
+        assert c.slot_timing(2).total_us > 0
+        c.set_timing(False)
+        assert_same_bits(c.process_mono8(img), want, "after timing was switched off")
+
+
 def test_float_stream_matches_single_calls(ctx, q):
     f, h, w = 7, 300, 420
     frames = np.stack([synth.s4_stress(h, w, 80 + i) for i in range(f)])
