@@ -289,6 +289,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(co
 #pragma unroll
     for (int k = 0; k < 4; ++k) xd[k] = 0.0;
   }
+  // generic exact path: the four products q[4i] * u of each of the lane's four columns, for the whole unit
+  double gcx[kMath == kMathGeneric ? 4 : 1][4];
+  if constexpr (kMath == kMathGeneric) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double du = (double)(a.border + c_base + 32 * k + lane);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        gcx[k][i] = __dmul_rn(Q.q[4 * i], du);
+        asm volatile("" : "+d"(gcx[k][i]));  // keep the products in registers: ptxas would recompute them per pixel
+      }
+    }
+  }
 
   const uint8_t *in_row = a.in + (size_t)f * a.frame_stride + (size_t)(a.border + r_base) * a.step;
   float4 *out_row = a.out + (size_t)f * a.out_frame_stride + (size_t)r_base * a.cw;
@@ -332,7 +345,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(co
         yslow = rect_axis_slow(yd);
       }
       float4 p[4];
-      points_of4<kMath>(Q, xd, yd, xslow, yslow, a.border + c_base + lane, a.border + r_base + r + j, dd[j], p);
+      if constexpr (kMath == kMathGeneric) {
+        const int v = a.border + r_base + r + j, u0 = a.border + c_base + lane;
+        const double dv = (double)v;
+        double gry[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gry[i] = __dmul_rn(Q.q[4 * i + 1], dv);
+        bool slow[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = reproject_exact_generic_hoisted(Q.q, gcx[k], gry, dd[j][k], slow[k]);
+        if (__builtin_expect(slow[0] || slow[1] || slow[2] || slow[3], 0)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (slow[k]) p[k] = reproject_exact_slow(Q.q, u0 + 32 * k, v, dd[j][k]);
+        }
+      } else {
+        points_of4<kMath>(Q, xd, yd, xslow, yslow, a.border + c_base + lane, a.border + r_base + r + j, dd[j], p);
+      }
       float4 *o = out_row + (size_t)j * a.cw + c_base + lane;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -1113,7 +1142,8 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
     // L2 prefetch distance in units (~4100 units are in flight; measured plateau 256-2048)
     a.prefetch_dist = L.prefetch_dist < 0 ? 0 : (L.prefetch_dist > 0 ? L.prefetch_dist : 512);
   }
-  const int min_blocks = L.ctas_per_sm > 0 ? L.ctas_per_sm : 7;
+  // the generic exact path keeps 16 column products in registers: 4 CTAs per SM (<= 128 registers)
+  const int min_blocks = L.ctas_per_sm > 0 ? L.ctas_per_sm : (math == kMathGeneric && !compact ? 4 : 7);
   if (launches) *launches += 1;
 
 #define D2PC_DISPATCH(T)                                                          \

@@ -142,6 +142,41 @@ def test_golden_fixture_cv2(ctx):
     ctx.set_q(_default_q())
 
 
+def test_generic_q_zero_disparities_stay_straight_line(ctx):
+    """The generic-Q arithmetic answers W == +-0 without the exact fall-back: +-inf by sign(numerator) ^ sign(W),
+    NaN (x86 pattern) where the numerator is zero as well.  Frames that are half zeros, with -0.0f, inf, NaN and
+    denormal disparities mixed in, under Q matrices that make W +0, -0 and non-zero for d == 0."""
+    rng = np.random.default_rng(77)
+    d = synth.s4_stress(240, 520, 9)
+    d[rng.random(d.shape) < 0.5] = 0.0
+    d[rng.random(d.shape) < 0.02] = -0.0
+    for v in (np.inf, -np.inf, np.nan, 1e-42, -1e-42, 3.0e38):
+        d[rng.integers(0, d.shape[0], 40), rng.integers(0, d.shape[1], 40)] = np.float32(v)
+    qs = {"default (W = +0)": _default_q().copy()}
+    qneg = _default_q().copy()       # every term of W is -0 for d == +0
+    qneg[3, 0] = -0.0
+    qneg[3, 1] = -0.0
+    qneg[3, 2] = -abs(qneg[3, 2])
+    qneg[3, 3] = -0.0
+    qs["W = -0"] = qneg
+    qgen = golden("reproject_golden.npz")["q_generic"].copy()
+    qs["generic"] = qgen
+    qz = qgen.copy()                 # W == 0 for d == 0 under a full matrix; X numerator 0 on the column u == 100
+    qz[3, 0] = 0.0
+    qz[3, 1] = 0.0
+    qz[3, 3] = 0.0
+    qz[0] = [1.0, 0.0, 0.0, -100.0]
+    qs["generic, q33 = 0, zero numerators"] = qz
+    ctx.set_tuning("force_generic", 1)
+    try:
+        for name, q in qs.items():
+            ctx.set_q(q)
+            assert_same_bits(ctx.process_f32(d), oracle.disparity_cb_f32(d, q), name)
+    finally:
+        ctx.set_tuning("force_generic", 0)
+        ctx.set_q(_default_q())
+
+
 @pytest.mark.parametrize("knob", ["force_scalar", "force_generic", "exact_variant"])
 def test_alternate_code_paths_agree(ctx, knob):
     ctx.set_q(_default_q())

@@ -94,11 +94,14 @@ def generic(argv):
         n = (w - 80) * (h - 80)
         d_in = float_batch(w, h, f)
         d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
-        for gen in (0, 1):
+        for gen, ctas in [(0, 0), (1, 0)] + [(1, int(c)) for c in argv]:
             ctx.set_tuning("force_generic", gen)
+            ctx.set_tuning("ctas_per_sm", ctas)
             s = t(lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4, d_out.data_ptr(), n * 16))
-            print(w, h, f, "generic" if gen else "rectified", "%.1f us  frac %.3f" % (s * 1e6, 20 * n * f / s / 1e9 / PEAK), flush=True)
+            print(w, h, f, "generic" if gen else "rectified", "ctas_per_sm", ctas or "default",
+                  "%.1f us  frac %.3f" % (s * 1e6, 20 * n * f / s / 1e9 / PEAK), flush=True)
         ctx.set_tuning("force_generic", 0)
+        ctx.set_tuning("ctas_per_sm", 0)
 
 
 def median(argv):
