@@ -96,7 +96,7 @@ struct d2pc_ctx {
   // tuning / test hooks
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0, median_variant = 0;
   bool force_scalar = false, force_generic = false;
-  int compact_variant = 0, exact_variant = 0, prefetch_dist = 0;
+  int compact_variant = 0, exact_variant = 0, prefetch_dist = 0, zero_numer = 0;
   bool timing = false;  // d2pc_set_timing: slot events carry timestamps
   std::vector<std::pair<uintptr_t, bool>> pin_cache;  // host pointer -> pinned (cudaHostAlloc / cudaHostRegister)?
   uint64_t pin_cache_gen = 0;                         // value of g_host_gen the cache was filled under
@@ -340,6 +340,7 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
   L.force_generic = ctx->force_generic;
   L.compact_variant = ctx->compact_variant;
   L.exact_variant = ctx->exact_variant;
+  L.zero_numer = ctx->zero_numer;
   L.prefetch_dist = ctx->prefetch_dist;
   CU(ctx, launch_reproject(L, stream, &nl));
   ctx->launches += nl;
@@ -665,6 +666,7 @@ int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value) {
   else if (k == "force_generic") ctx->force_generic = value != 0;
   else if (k == "force_park" || k == "compact_variant") ctx->compact_variant = value;
   else if (k == "exact_variant") ctx->exact_variant = value;
+  else if (k == "zero_numer") ctx->zero_numer = value;
   else if (k == "prefetch_dist") ctx->prefetch_dist = value;
   else if (k == "median_ksize") {
     if (value < 1 || value > 15 || !(value & 1)) return D2PC_ERR_INVALID_ARG;

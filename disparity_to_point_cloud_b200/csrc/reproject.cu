@@ -62,8 +62,12 @@ struct ReprojArgs {
   QParams Q;
 };
 
-enum { kMathRect0 = 0, kMathRectW = 1, kMathGeneric = 2, kMathFast = 3, kMathRect0M = 4 };  // M: Markstein quotients
-#define D2PC_IS_RECT(m) ((m) == kMathRect0 || (m) == kMathRectW || (m) == kMathRect0M)
+// M: Markstein quotients.  Z: kMathRect0 for a calibration whose principal point column is an image column (X is
+// exactly 0 there): zero numerators stay on the straight-line path instead of taking the exact function -- 4-25 %
+// faster for such a Q, 2-4 % slower for any other (a few more instructions per pixel), hence chosen on the host.
+enum { kMathRect0 = 0, kMathRectW = 1, kMathGeneric = 2, kMathFast = 3, kMathRect0M = 4, kMathRect0Z = 5 };
+#define D2PC_IS_RECT(m) ((m) == kMathRect0 || (m) == kMathRectW || (m) == kMathRect0M || (m) == kMathRect0Z)
+#define D2PC_IS_GUARD(m) ((m) == kMathRect0 || (m) == kMathRect0Z)
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
   float4 v;
@@ -141,15 +145,18 @@ __device__ __forceinline__ float load1<uint8_t>(const uint8_t *row, int col, flo
 
 // Four pixels of one lane (columns u0, u0+32, u0+64, u0+96 of row v): the arithmetic is straight-line so the
 // four FP64 dependency chains interleave; the rare slow path is one warp-level branch afterwards.
+// xslow: bit k = column k of the lane must take the exact function, bit 4 + k = its numerator is +-0 (exact
+// function only where the disparity is zero as well); yslow: bit 0 / bit 1, the same for the row.
 template <int kMath>
 __device__ __forceinline__ void points_of4(const QParams &Q, const double (&xd)[4], double yd, uint32_t xslow,
-                                           bool yslow, int u0, int v, const float (&d)[4], float4 (&p)[4]) {
+                                           uint32_t yslow, int u0, int v, const float (&d)[4], float4 (&p)[4]) {
   if constexpr (D2PC_IS_RECT(kMath)) {
     bool slow[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      p[k] = reproject_exact_rectified<kMath != kMathRectW, kMath == kMathRect0>(
-          Q, xd[k], yd, yslow || ((xslow >> k) & 1u), d[k], slow[k]);
+      p[k] = reproject_exact_rectified<kMath != kMathRectW, D2PC_IS_GUARD(kMath), kMath == kMathRect0Z>(
+          Q, xd[k], yd, ((yslow | (xslow >> k)) & 1u) != 0u, (((yslow >> 1) | (xslow >> (4 + k))) & 1u) != 0u, d[k],
+          slow[k]);
     if (__builtin_expect(slow[0] || slow[1] || slow[2] || slow[3], 0)) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -221,8 +228,9 @@ __device__ __forceinline__ float4 point_of(const QParams &Q, int u, int v, float
   if constexpr (D2PC_IS_RECT(kMath)) {
     const double xd = rect_axis_const(u, Q.q03), yd = rect_axis_const(v, Q.q13);
     bool slow;
-    float4 p = reproject_exact_rectified<kMath != kMathRectW, kMath == kMathRect0>(
-        Q, xd, yd, rect_axis_slow(xd) || rect_axis_slow(yd) || Q.zd_slow, d, slow);
+    float4 p = reproject_exact_rectified<kMath != kMathRectW, D2PC_IS_GUARD(kMath), kMath == kMathRect0Z>(
+        Q, xd, yd, rect_axis_slow_t<kMath == kMathRect0Z>(xd) || rect_axis_slow_t<kMath == kMathRect0Z>(yd) || Q.zd_slow,
+        rect_axis_zero(xd) || rect_axis_zero(yd), d, slow);
     if (__builtin_expect(slow, 0)) p = reproject_exact_slow(Q.q, u, v, d);
     return p;
   } else if constexpr (kMath == kMathGeneric) {
@@ -281,7 +289,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(co
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       xd[k] = rect_axis_const(a.border + c_base + 32 * k + lane, Q.q03);
-      xslow |= rect_axis_slow(xd[k]) ? (1u << k) : 0u;
+      xslow |= rect_axis_slow_t<kMath == kMathRect0Z>(xd[k]) ? (1u << k) : 0u;
+      if constexpr (kMath == kMathRect0Z) xslow |= rect_axis_zero(xd[k]) ? (16u << k) : 0u;
     }
     if (Q.zd_slow) xslow = 0xfu;
     yd_lane = rect_axis_const(a.border + r_base + lane, Q.q13);
@@ -339,10 +348,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(co
     for (int j = 0; j < 2; ++j) {
       if (r + j >= rows) break;
       double yd = 0.0;
-      bool yslow = false;
+      uint32_t yslow = 0;
       if constexpr (D2PC_IS_RECT(kMath)) {
         yd = __shfl_sync(0xffffffffu, yd_lane, r + j);
-        yslow = rect_axis_slow(yd);
+        yslow = rect_axis_slow_t<kMath == kMathRect0Z>(yd) ? 1u : 0u;
+        if constexpr (kMath == kMathRect0Z) yslow |= rect_axis_zero(yd) ? 2u : 0u;
       }
       float4 p[4];
       if constexpr (kMath == kMathGeneric) {
@@ -407,18 +417,20 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
 }
 
 // (double)(float)(i + q) for every image column / row, computed once per launch.  Entries the straight-line path
-// must not use (+-0, inf, NaN numerators: rect_axis_slow) are stored as NaN so consumers test one exponent field;
-// the slow path recomputes from Q and never reads the table.  xtab is padded by kSegCols entries.
-__global__ void rect_tables_kernel(double q03, double q13, int width, int height, double *xtab, double *ytab) {
+// must not use (tiny, inf, NaN numerators, and +-0 unless zero_ok: rect_axis_slow / rect_axis_slow_nz) are stored as
+// NaN so consumers test one exponent field; the slow path recomputes from Q and never reads the table.  xtab is
+// padded by kSegCols entries.
+__global__ void rect_tables_kernel(double q03, double q13, int width, int height, bool zero_ok, double *xtab,
+                                   double *ytab) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
   if (i < width + kSegCols) {
     const double x = rect_axis_const(i, q03);
-    xtab[i] = rect_axis_slow(x) ? qnan : x;
+    xtab[i] = (zero_ok ? rect_axis_slow_nz(x) : rect_axis_slow(x)) ? qnan : x;
   }
   if (i < height) {
     const double y = rect_axis_const(i, q13);
-    ytab[i] = rect_axis_slow(y) ? qnan : y;
+    ytab[i] = (zero_ok ? rect_axis_slow_nz(y) : rect_axis_slow(y)) ? qnan : y;
   }
 }
 
@@ -482,17 +494,18 @@ __global__ void __launch_bounds__(kCThreads, 4) reproject_compact_kernel(const _
     }
     const int v = a.border + crow[m], u0 = a.border + c_base[m] + lane;
     double xd[4] = {0.0, 0.0, 0.0, 0.0}, yd = 0.0;
-    uint32_t xslow = 0;
-    bool yslow = false;
+    uint32_t xslow = 0, yslow = 0;
     if constexpr (D2PC_IS_RECT(kMath)) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         xd[k] = a.xtab[u0 + 32 * k];  // padded table; NaN marks numerators for the slow path
         xslow |= (((uint32_t)__double2hiint(xd[k]) & 0x7ff00000u) == 0x7ff00000u) ? (1u << k) : 0u;
+        if constexpr (kMath == kMathRect0Z) xslow |= rect_axis_zero(xd[k]) ? (16u << k) : 0u;
       }
       if (Q.zd_slow) xslow = 0xfu;
       yd = a.ytab[v];
-      yslow = ((uint32_t)__double2hiint(yd) & 0x7ff00000u) == 0x7ff00000u;
+      yslow = (((uint32_t)__double2hiint(yd) & 0x7ff00000u) == 0x7ff00000u) ? 1u : 0u;
+      if constexpr (kMath == kMathRect0Z) yslow |= rect_axis_zero(yd) ? 2u : 0u;
     }
     float4 p[4];
     points_of4<kMath>(Q, xd, yd, xslow, yslow, u0, v, dd, p);
@@ -653,8 +666,9 @@ __device__ __forceinline__ void cp_async_16_zfill(void *smem_dst, const void *gm
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 
-// kW warps per CTA (8 is what ships: four 46 KB CTAs per SM).
-template <typename InT, bool kVec, int kMinB, int kW>
+// kW warps per CTA (8 is what ships: four 46 KB CTAs per SM).  kZN: zero numerators stay straight-line (kMathRect0Z);
+// a zero disparity is dropped here whatever its numerators, so no 0 / 0 case exists.
+template <typename InT, bool kVec, int kMinB, int kW, bool kZN = false>
 __global__ void __launch_bounds__(kW * 32, kMinB) reproject_compact_band_kernel(const __grid_constant__ ReprojArgs a) {
   constexpr int kT = kW * 32;
   extern __shared__ __align__(16) float sd[];  // [band_rows][cw_pad]
@@ -747,7 +761,7 @@ __global__ void __launch_bounds__(kW * 32, kMinB) reproject_compact_band_kernel(
   }
   if ((int)threadIdx.x < R) {  // row numerators; NaN marks a row the straight-line path must not use
     const double y = rect_axis_const(a.border + row0 + (int)threadIdx.x, Q.q13);
-    syd[threadIdx.x] = rect_axis_slow(y) ? __longlong_as_double(0x7ff8000000000000ll) : y;
+    syd[threadIdx.x] = rect_axis_slow_t<kZN>(y) ? __longlong_as_double(0x7ff8000000000000ll) : y;
   }
   asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -884,7 +898,7 @@ __global__ void __launch_bounds__(kW * 32, kMinB) reproject_compact_band_kernel(
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       xd[k] = rect_axis_const(u0 + 32 * k, Q.q03);
-      xslow |= rect_axis_slow(xd[k]) ? (1u << k) : 0u;
+      xslow |= rect_axis_slow_t<kZN>(xd[k]) ? (1u << k) : 0u;
     }
     for (int r = r_lo; r < r_hi; ++r) {
       const double yd = syd[r];
@@ -924,12 +938,13 @@ cudaError_t launch_compact(K kernel, const ReprojArgs &a, int grid, cudaStream_t
 template <typename InT, int kMath>
 cudaError_t launch_typed(const ReprojArgs &a, bool vec, bool compact, int grid, int min_blocks, cudaStream_t s) {
   if (compact) {
-    if constexpr (kMath == kMathRect0) {
+    if constexpr (D2PC_IS_GUARD(kMath)) {
       if (a.d_sure_bits != 0 && a.band_rows > 0) {  // band kernel
+        constexpr bool kZN = kMath == kMathRect0Z;
         const size_t smem = (size_t)a.band_rows * a.cw_pad * sizeof(float);
-        auto kern = !vec ? reproject_compact_band_kernel<InT, false, 3, 8>
-                         : (min_blocks == 3 ? reproject_compact_band_kernel<InT, true, 3, 8>
-                                            : reproject_compact_band_kernel<InT, true, 4, 8>);
+        auto kern = !vec ? reproject_compact_band_kernel<InT, false, 3, 8, kZN>
+                         : (min_blocks == 3 ? reproject_compact_band_kernel<InT, true, 3, 8, kZN>
+                                            : reproject_compact_band_kernel<InT, true, 4, 8, kZN>);
         if (smem > 48 * 1024) {
           cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           if (e != cudaSuccess) return e;
@@ -1048,9 +1063,16 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
                    (L.frame_stride % valign == 0) && ((size_t)L.border * esz % valign == 0) &&
                    (cw % 4 == 0 || L.border >= 3) && !L.force_scalar;
 
+  // X is exactly zero on an image column (an integral principal point): keep that column straight-line
+  auto zero_column = [&]() {
+    const double c = std::nearbyint(-a.Q.q03);
+    return c >= 0.0 && c < (double)L.width && (float)(c + a.Q.q03) == 0.0f;
+  };
+  const bool zero_numer = L.zero_numer > 0 || (L.zero_numer == 0 && zero_column());
   const int math = L.arith_fast ? kMathFast
                    : (a.Q.rectified && !L.force_generic
-                          ? (a.Q.q33_zero ? (L.exact_variant == 1 ? kMathRect0M : kMathRect0) : kMathRectW)
+                          ? (a.Q.q33_zero ? (L.exact_variant == 1 ? kMathRect0M : (zero_numer ? kMathRect0Z : kMathRect0))
+                                          : kMathRectW)
                           : kMathGeneric);
   const bool compact = L.compact;
 
@@ -1070,7 +1092,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
     grid = (int)total;  // one CTA per tile; the ticket, not blockIdx, names the tile
     cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    if (math == kMathRect0 && !a.Q.zd_slow && L.compact_variant != 1) {
+    if (D2PC_IS_GUARD(math) && !a.Q.zd_slow && L.compact_variant != 1) {
       // |n| <= max_numer for every numerator of the frame; |q| = |n| / (|q32| * |d|) < 2^127 once
       // |d| >= max_numer * 2^-127 / |q32|; doubled for margin, clamped to the smallest normal float.
       const double aq32 = a.Q.q32 < 0 ? -a.Q.q32 : a.Q.q32;
@@ -1119,8 +1141,8 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
     }
     if (a.Q.rectified && !L.arith_fast && !L.force_generic && a.band_rows == 0) {
       const int n = (int)(L.width + kSegCols > L.height ? L.width + kSegCols : L.height);
-      rect_tables_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a.Q.q03, a.Q.q13, (int)L.width, (int)L.height, tabs,
-                                                            tabs + L.width + kSegCols);
+      rect_tables_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a.Q.q03, a.Q.q13, (int)L.width, (int)L.height,
+                                                            math == kMathRect0Z, tabs, tabs + L.width + kSegCols);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       if (launches) *launches += 1;
     }
@@ -1149,6 +1171,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
 #define D2PC_DISPATCH(T)                                                          \
   switch (math) {                                                                 \
     case kMathRect0: return launch_typed<T, kMathRect0>(a, vec, compact, grid, min_blocks, stream); \
+    case kMathRect0Z: return launch_typed<T, kMathRect0Z>(a, vec, compact, grid, min_blocks, stream); \
     case kMathRect0M: return launch_typed<T, kMathRect0M>(a, vec, compact, grid, min_blocks, stream); \
     case kMathRectW: return launch_typed<T, kMathRectW>(a, vec, compact, grid, min_blocks, stream); \
     case kMathGeneric: return launch_typed<T, kMathGeneric>(a, vec, compact, grid, min_blocks, stream); \

@@ -46,6 +46,7 @@ struct ReprojectLaunch {
   bool force_scalar = false;   // exercise the unaligned load path
   bool force_generic = false;  // exercise the generic-Q exact path on a rectified Q
   int exact_variant = 0;       // rectified exact quotients: 0 = guarded multiply (7 FP64 ops), 1 = Markstein (15)
+  int zero_numer = 0;          // zero-numerator columns straight-line: 0 = when Q has one in the image, 1 always, -1 never
   int compact_variant = 0;     // CROP_FINITE kernel: 0 = automatic (band where Q allows, else park),
                                // 1 = park-then-compact for every Q (test hook for the fallback)
   int prefetch_dist = 0;       // L2 prefetch distance: CROP kernel in work units, band kernel in tiles

@@ -177,6 +177,61 @@ def test_generic_q_zero_disparities_stay_straight_line(ctx):
         ctx.set_q(_default_q())
 
 
+@pytest.mark.parametrize("q32,q33", [(1.0 / 0.09, 0.0), (-1.0 / 0.09, -0.0), (-7.25, 0.37)])
+def test_integral_principal_point_zero_numerators(ctx, q32, q33):
+    """A calibration whose principal point falls on a pixel: X is exactly 0 on the column u == cx and Y on the row
+    v == cy.  The guarded-multiply paths keep those pixels straight-line (0 * r is the IEEE quotient, sign included;
+    0 / 0 where the disparity is zero as well is x86's NaN); the Markstein variant and q33 != 0 send them to the
+    exact function.  Every code path, CROP and CROP_FINITE, against the oracle."""
+    import disparity_to_point_cloud_b200 as d2pc
+    q = np.array([[1, 0, 0, -376.0], [0, 1, 0, -240.0], [0, 0, 0, 713.5], [0, 0, q32, q33]], dtype=np.float64)
+    rng = np.random.default_rng(5)
+    d = synth.s4_stress(480, 752, 11)
+    d[rng.random(d.shape) < 0.2] = 0.0
+    d[rng.random(d.shape) < 0.02] = -0.0
+    d[240, ::3] = 0.0                     # zeros on the Y == 0 row and the X == 0 column: 0 / 0
+    d[::5, 376] = 0.0
+    d[240, 376] = 2.5
+    for v in (np.inf, -np.inf, np.nan, 1e-42, 3.0e38, -4.0):
+        d[rng.integers(0, 480, 30), rng.integers(0, 752, 30)] = np.float32(v)
+        d[240, rng.integers(40, 712, 3)] = np.float32(v)
+        d[rng.integers(40, 440, 3), 376] = np.float32(v)
+    want = oracle.disparity_cb_f32(d, q)
+    ctx.set_q(q)
+    try:
+        # zero_numer: 0 picks the zero-numerator kernel variant for this Q, -1 forces the ordinary one (that column
+        # then takes the exact function), 1 is what a Q without such a column never sees
+        for knobs in ({}, {"zero_numer": -1}, {"zero_numer": 1, "force_scalar": 1}, {"force_scalar": 1},
+                      {"exact_variant": 1}, {"force_generic": 1}, {"rows_per_unit": 3}):
+            for k, v in knobs.items():
+                ctx.set_tuning(k, v)
+            try:
+                assert_same_bits(ctx.process_f32(d), want, f"CROP {knobs}")
+                ctx.set_filter_mode(d2pc.FILTER_CROP_FINITE)
+                for park in (0, 1):
+                    ctx.set_tuning("force_park", park)
+                    assert_same_bits(ctx.process_f32(d), oracle.filter_finite(want), f"CROP_FINITE park={park} {knobs}")
+            finally:
+                ctx.set_filter_mode(d2pc.FILTER_CROP)
+                ctx.set_tuning("force_park", 0)
+                for k in knobs:
+                    ctx.set_tuning(k, 0)
+        # the mono8 callback (bytes / 8) through the same Q
+        img = synth.s2_scene(480, 752, 4)
+        assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, q), "mono8")
+        # and the zero-numerator variant under the default Q (zero row v == 240, no zero column)
+        ctx.set_q(_default_q())
+        ctx.set_tuning("zero_numer", 1)
+        assert_same_bits(ctx.process_f32(d), oracle.disparity_cb_f32(d, _default_q()), "default Q, zero_numer=1")
+        ctx.set_filter_mode(d2pc.FILTER_CROP_FINITE)
+        assert_same_bits(ctx.process_f32(d), oracle.filter_finite(oracle.disparity_cb_f32(d, _default_q())),
+                         "default Q, zero_numer=1, CROP_FINITE")
+    finally:
+        ctx.set_filter_mode(d2pc.FILTER_CROP)
+        ctx.set_tuning("zero_numer", 0)
+        ctx.set_q(_default_q())
+
+
 @pytest.mark.parametrize("knob", ["force_scalar", "force_generic", "exact_variant"])
 def test_alternate_code_paths_agree(ctx, knob):
     ctx.set_q(_default_q())

@@ -87,6 +87,33 @@ def compact(argv):
         ctx.set_filter_mode(0)
 
 
+def numer(argv):
+    """Cost of the degenerate numerator column / row (u == cx, v == cy): the same kernels with the principal point
+    moved out of the image, where no pixel has a zero numerator."""
+    ctx = d2pc.Context()
+    t = timer(ctx)
+    for (w, h, f) in [(1280, 720, 64), (3840, 2160, 16), (752, 480, 256)]:
+        n = (w - 80) * (h - 80)
+        d_in = float_batch(w, h, f)
+        d_out = torch.empty((f, n * 16), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(f, dtype=torch.int32, device="cuda")
+        for mode in (0, 1):
+            ctx.set_filter_mode(mode)
+            for name, (cx, cy), zn in (("cx,cy inside", (376.0, 240.0), 0), ("cx,cy inside, ordinary kernel", (376.0, 240.0), -1),
+                                       ("cx,cy outside", (-5000.5, -5000.5), 0),
+                                       ("cx,cy outside, zero-numerator kernel", (-5000.5, -5000.5), 1)):
+                q = np.array([[1, 0, 0, -cx], [0, 1, 0, -cy], [0, 0, 0, 714.24], [0, 0, 1 / 0.09, 0]], dtype=np.float64)
+                ctx.set_q(q)
+                ctx.set_tuning("zero_numer", zn)
+                s = t(lambda: ctx.reproject_f32_device(d_in.data_ptr(), f, w, h, w * 4, w * h * 4, d_out.data_ptr(), n * 16,
+                                                       d_cnt.data_ptr() if mode else 0))
+                kept = int(d_cnt.sum().item()) if mode else n * f
+                by = 4 * n * f + 16 * kept
+                print(w, h, f, "CROP_FINITE" if mode else "CROP", name, "%.1f us  frac %.3f" % (s * 1e6, by / s / 1e9 / PEAK), flush=True)
+        ctx.set_filter_mode(0)
+        ctx.set_tuning("zero_numer", 0)
+
+
 def generic(argv):
     ctx = d2pc.Context()
     t = timer(ctx)
@@ -192,7 +219,7 @@ def stream(argv):
 
 
 if __name__ == "__main__":
-    cmds = {"crop": crop, "compact": compact, "generic": generic, "median": median, "score": score, "latency": latency,
+    cmds = {"crop": crop, "compact": compact, "generic": generic, "numer": numer, "median": median, "score": score, "latency": latency,
             "stream": stream}
     if len(sys.argv) < 2 or sys.argv[1] not in cmds:
         raise SystemExit(__doc__)
