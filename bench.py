@@ -306,11 +306,12 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 # product arm
 # ---------------------------------------------------------------------------------------------------------
-def pcie_ceiling(torch, world, h2d_bytes, d2h_bytes, seconds=0.5):
+def pcie_ceiling(torch, world, h2d_bytes, d2h_bytes, seconds=0.5, direction="both", n_buf=3):
     """Raw pinned cudaMemcpyAsync traffic of the e2e path's shape -- h2d_bytes in and d2h_bytes out per unit, two
     streams, nothing else -- on every rank at once.  -> (GB/s summed over ranks and directions, units/s)."""
     from disparity_to_point_cloud_b200 import pcie
-    return pcie.measure(torch, world, h2d_bytes, d2h_bytes, seconds, barrier_sync, max_over_ranks, sum_over_ranks)
+    return pcie.measure(torch, world, h2d_bytes, d2h_bytes, seconds, barrier_sync, max_over_ranks, sum_over_ranks,
+                        n_buf=n_buf, direction=direction)
 
 
 def run_ours(args):
@@ -485,11 +486,19 @@ def run_ours(args):
            "stagger_us": args.stagger_us}
     pin.free()
     if not args.no_ceiling:
-        ceil_gbs, ceil_units = pcie_ceiling(torch, world, in_bytes, out_bytes)
+        ceil_gbs, ceil_units = pcie_ceiling(torch, world, in_bytes, out_bytes, n_buf=max(args.slots, 3))
         e2e["ceiling_gbs"] = ceil_gbs
         e2e["frac_of_ceiling"] = e2e["gbs"] / ceil_gbs if ceil_gbs else None
-        e2e["ceiling_note"] = ("plain pinned cudaMemcpyAsync, %d B in + %d B out per unit on two streams, all %d rank(s) "
-                               "at once, no kernels" % (in_bytes, out_bytes, world))
+        e2e["ceiling_note"] = ("plain pinned cudaMemcpyAsync, %d B in + %d B out per unit on two free-running streams, "
+                               "all %d rank(s) at once, no kernels" % (in_bytes, out_bytes, world))
+        # the bound no schedule can beat: each direction alone (two free-running streams contend more than the
+        # pipeline's partially overlapped copies do, so a unit with comparable traffic each way can exceed `ceiling`)
+        _, u_in = pcie_ceiling(torch, world, in_bytes, out_bytes, 0.3, "h2d", max(args.slots, 3))
+        _, u_out = pcie_ceiling(torch, world, in_bytes, out_bytes, 0.3, "d2h", max(args.slots, 3))
+        bound = min(u_in, u_out)
+        e2e["one_way_bound_units_per_s"] = bound
+        e2e["one_way_bound_direction"] = "h2d" if u_in < u_out else "d2h"
+        e2e["frac_of_one_way_bound"] = e2e["frames_per_s"] / bound if bound else None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -535,7 +544,7 @@ def main():
     ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS), help="BASELINE workload (SURVEY 8 numbering)")
     ap.add_argument("--frames", type=int, default=0, help="units per GPU per step (0 = the config's own)")
     ap.add_argument("--e2e-frames", type=int, default=0, help="units timed end to end (0 = one full step, >= 256)")
-    ap.add_argument("--slots", type=int, default=3, help="pipeline slots per GPU of the end-to-end path")
+    ap.add_argument("--slots", type=int, default=4, help="pipeline slots per GPU of the end-to-end path")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: per-step units per GPU; strong: per-step units in total, sharded i mod G")
     ap.add_argument("--stagger-us", type=int, default=0, help="experiment: rank r starts its end-to-end stream r x this late")

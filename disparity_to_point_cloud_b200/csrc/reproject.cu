@@ -152,11 +152,17 @@ __device__ __forceinline__ void points_of4(const QParams &Q, const double (&xd)[
                                            uint32_t yslow, int u0, int v, const float (&d)[4], float4 (&p)[4]) {
   if constexpr (D2PC_IS_RECT(kMath)) {
     bool slow[4];
+    const bool ys = (yslow & 1u) != 0u, yz = (yslow & 2u) != 0u;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      p[k] = reproject_exact_rectified<kMath != kMathRectW, D2PC_IS_GUARD(kMath), kMath == kMathRect0Z>(
-          Q, xd[k], yd, ((yslow | (xslow >> k)) & 1u) != 0u, (((yslow >> 1) | (xslow >> (4 + k))) & 1u) != 0u, d[k],
-          slow[k]);
+    for (int k = 0; k < 4; ++k) {
+      if constexpr (kMath == kMathRect0Z)
+        p[k] = reproject_exact_rectified<true, true, true>(Q, xd[k], yd, ys || ((xslow >> k) & 1u),
+                                                           yz || ((xslow >> (4 + k)) & 1u), d[k], slow[k]);
+      else
+        p[k] = reproject_exact_rectified<kMath != kMathRectW, kMath == kMathRect0>(Q, xd[k], yd,
+                                                                                   ys || ((xslow >> k) & 1u), false,
+                                                                                   d[k], slow[k]);
+    }
     if (__builtin_expect(slow[0] || slow[1] || slow[2] || slow[3], 0)) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)

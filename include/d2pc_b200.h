@@ -93,7 +93,7 @@ typedef struct d2pc_config {
   /* capacity / pipeline */
   int32_t max_width, max_height; /* largest frame the context will see (buffers are sized once) */
   int32_t max_batch;             /* frames per batched call chunk */
-  int32_t n_slots;               /* async pipeline depth (>= 1, default 3) */
+  int32_t n_slots;               /* async pipeline depth (>= 1, default 4) */
 } d2pc_config;
 
 typedef struct d2pc_ctx d2pc_ctx;

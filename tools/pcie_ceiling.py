@@ -21,14 +21,18 @@ def main():
     rank, world, local = bench.dist_setup()
     torch.cuda.set_device(local)
     shapes = {"config4 3840x2160 f32": (3840 * 2160 * 4, bench.n_points(3840, 2160) * 16),
-              "config2 752x480 mono8": (752 * 480, bench.n_points(752, 480) * 16)}
+              "config2 752x480 mono8": (752 * 480, bench.n_points(752, 480) * 16),
+              "config5 4 x 1280x720 mono8 -> 665x665 cloud": (4 * 1280 * 720, 5475600)}
+    n_bufs = [int(x) for x in sys.argv[1:]] or [3]
     for name, (bi, bo) in shapes.items():
         for direction in ("h2d", "d2h", "both"):
-            gbs, units = pcie.measure(torch, world, bi, bo, 0.6, bench.barrier_sync, bench.max_over_ranks,
-                                      bench.sum_over_ranks, direction=direction)
-            if rank == 0:
-                print(json.dumps({"shape": name, "direction": direction, "n_gpus": world, "GB/s_total": round(gbs, 2),
-                                  "GB/s_per_gpu": round(gbs / world, 2), "frames/s_total": round(units, 1)}), flush=True)
+            for n_buf in n_bufs:
+                gbs, units = pcie.measure(torch, world, bi, bo, 0.6, bench.barrier_sync, bench.max_over_ranks,
+                                          bench.sum_over_ranks, n_buf=n_buf, direction=direction)
+                if rank == 0:
+                    print(json.dumps({"shape": name, "direction": direction, "n_gpus": world, "n_buf": n_buf,
+                                      "GB/s_total": round(gbs, 2), "GB/s_per_gpu": round(gbs / world, 2),
+                                      "frames/s_total": round(units, 1)}), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

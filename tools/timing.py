@@ -8,9 +8,12 @@
     python tools/timing.py score                          MatchingScoreCb1/2 (device entry)
     python tools/timing.py latency                        synchronous per-call latency of the host entry points
     python tools/timing.py stream                         end-to-end stream throughput vs pipeline depth
+    python tools/timing.py fusion [slots...]              config 5: frame sets / s vs slots, spans of one set, submit cost
+    python tools/timing.py numer                          cost of an integral principal point, both kernel variants
 
 Kernel timings use CUDA events on the context's compute stream after warm-up.
 """
+import ctypes
 import statistics
 import sys
 import time
@@ -218,9 +221,65 @@ def stream(argv):
         pin.free()
 
 
+def fusion(argv):
+    """Config 5 stream: frame sets per second vs slots, the spans of one set, and the CPU time of a submission."""
+    w, h, nsets = 1280, 720, 1500
+    pin = d2pc.PinnedArray((4, 4, h, w), np.uint8)
+    for i in range(4):
+        for j in range(4):
+            pin.array[i, j] = synth.s2_scene(h, w, 10 * i + j)
+    for slots in [int(x) for x in argv] or (2, 3, 4, 6):
+        ctx = d2pc.Context(n_slots=slots, offset_x=-7, offset_y=15)
+        for pre in (False, True):   # without / with MatchingScoreCb1/2 (two 21 us kernels less per set)
+            ctx.process_fusion_stream(pin.array, collect=False, preprocess_scores=pre)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.process_fusion_stream(pin.array, collect=False, n_sets=nsets, preprocess_scores=pre)
+            torch.cuda.synchronize()
+            s = time.perf_counter() - t0
+            if not pre:
+                print(f"   scores already preprocessed: {nsets/s:8.1f} sets/s")
+        # one set alone with the spans, then the host cost of a submission with the slot already idle
+        ctx.set_timing(True)
+        ctx.submit_fusion(0, *pin.array[0])
+        ctx.wait(0)
+        t = ctx.slot_timing(0)
+        ctx.set_timing(False)
+        cpu = []
+        for i in range(50):
+            t1 = time.perf_counter()
+            ctx.submit_fusion(0, *pin.array[i % 4])
+            cpu.append(time.perf_counter() - t1)
+            ctx.wait(0)
+        # the same pipeline driven from here with timing on: spans of a set while its neighbours are in flight
+        ctx.set_timing(True)
+        spans = []
+        sub = ret = 0
+        t2 = time.perf_counter()
+        while ret < 400:
+            while sub < 400 and sub - ret < slots:
+                ctx.submit_fusion(sub % slots, *pin.array[sub % 4])
+                sub += 1
+            cl = d2pc.Cloud()
+            assert d2pc.lib().d2pc_wait(ctx._h, ret % slots, ctypes.byref(cl)) == 0   # no copy of the cloud
+            ctx._keep.pop(ret % slots, None)
+            tt = ctx.slot_timing(ret % slots)
+            spans.append((tt.h2d_us, tt.kernels_us, tt.d2h_us, tt.total_us))
+            ret += 1
+        s2 = time.perf_counter() - t2
+        ctx.set_timing(False)
+        sp = np.median(np.array(spans[50:]), axis=0)
+        print(f"   in the pipeline (python loop, {400/s2:.0f} sets/s): h2d {sp[0]:.0f} kernels {sp[1]:.0f} d2h {sp[2]:.0f} total {sp[3]:.0f} us")
+        print(f"fusion {w}x{h} slots={slots}: {nsets/s:8.1f} sets/s ({1e6*s/nsets:6.1f} us/set); one set alone: h2d {t.h2d_us:.0f} "
+              f"kernels {t.kernels_us:.0f} d2h {t.d2h_us:.0f} total {t.total_us:.0f} us; submit call (python) "
+              f"{1e6*statistics.median(cpu):.0f} us", flush=True)
+        ctx.close()
+    pin.free()
+
+
 if __name__ == "__main__":
     cmds = {"crop": crop, "compact": compact, "generic": generic, "numer": numer, "median": median, "score": score, "latency": latency,
-            "stream": stream}
+            "stream": stream, "fusion": fusion}
     if len(sys.argv) < 2 or sys.argv[1] not in cmds:
         raise SystemExit(__doc__)
     cmds[sys.argv[1]](sys.argv[2:])
