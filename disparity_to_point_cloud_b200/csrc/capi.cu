@@ -97,6 +97,7 @@ struct d2pc_ctx {
   int rows_per_unit = 0, ctas_per_sm = 0, median_strip = 0, median_variant = 0;
   bool force_scalar = false, force_generic = false;
   int compact_variant = 0, exact_variant = 0, prefetch_dist = 0, zero_numer = 0;
+  int fuse_median = 0;  // mono8 callback as one fused launch where possible: 0 yes, -1 never (two launches)
   bool timing = false;  // d2pc_set_timing: slot events carry timestamps
   std::vector<std::pair<uintptr_t, bool>> pin_cache;  // host pointer -> pinned (cudaHostAlloc / cudaHostRegister)?
   uint64_t pin_cache_gen = 0;                         // value of g_host_gen the cache was filled under
@@ -288,8 +289,35 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
                     size_t step, size_t frame_stride, uint8_t *d_med, uint8_t *d_out, size_t out_stride,
                     uint32_t *d_counts, void *scratch, void *tables, uint32_t *ticket, cudaStream_t stream) {
   const d2pc_config &c = ctx->cfg;
-  const uint8_t *reproj_in = d_in;
   int nl = 0;
+  ReprojectLaunch L;
+  L.in = d_in;
+  L.in_is_f32 = is_f32;
+  L.step = step;
+  L.frame_stride = frame_stride;
+  L.n_frames = n_frames;
+  L.width = w;
+  L.height = h;
+  L.border = c.border;
+  L.scale = c.disparity_scale;
+  L.out = d_out;
+  L.out_stride_bytes = out_stride;
+  L.counts = d_counts;
+  L.Q = &ctx->Q;
+  L.arith_fast = c.arith_mode == D2PC_ARITH_FAST;
+  L.compact = c.filter_mode == D2PC_FILTER_CROP_FINITE;
+  L.scratch = scratch;
+  L.tables = tables;
+  L.ticket = ticket;
+  L.sm_count = ctx->sm_count;
+  L.rows_per_unit = ctx->rows_per_unit;
+  L.ctas_per_sm = ctx->ctas_per_sm;
+  L.force_scalar = ctx->force_scalar;
+  L.force_generic = ctx->force_generic;
+  L.compact_variant = ctx->compact_variant;
+  L.exact_variant = ctx->exact_variant;
+  L.zero_numer = ctx->zero_numer;
+  L.prefetch_dist = ctx->prefetch_dist;
   if (!is_f32 && c.median_ksize > 1) {
     // cpp:55-57: only crop pixels are consumed downstream, so only those medians are produced
     // (the replicate border is still the image edge, which matters when border < ksize/2).
@@ -309,39 +337,22 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
     M.sm_count = ctx->sm_count;
     M.strip_rows = ctx->median_strip;
     M.variant = ctx->median_variant;
+    // the whole callback in one launch where the arithmetic allows it (the default Q does): median -> x 1/8 ->
+    // reproject -> PointXYZ, no intermediate image
+    const bool fuse = ctx->fuse_median >= 0 && M.ow > 0 && M.oh > 0 && (c.median_ksize > 3 || M.variant != 0) &&
+                      reproject_fuses_with_median(L);
+    if (fuse) {
+      M.points = d_out;
+      M.points_stride_bytes = out_stride;
+      M.Q = &ctx->Q;
+      M.scale = c.disparity_scale;
+    }
     CU(ctx, launch_median_u8(M, stream, &nl));
     ctx->launches += nl;
-    reproj_in = d_med;
+    if (fuse) return D2PC_OK;
+    L.in = d_med;
   }
-  ReprojectLaunch L;
-  L.in = reproj_in;
-  L.in_is_f32 = is_f32;
-  L.step = step;
-  L.frame_stride = frame_stride;
-  L.n_frames = n_frames;
-  L.width = w;
-  L.height = h;
-  L.border = c.border;
-  L.scale = c.disparity_scale;
-  L.out = d_out;
-  L.out_stride_bytes = out_stride;
-  L.counts = d_counts;
-  L.Q = &ctx->Q;
-  L.arith_fast = c.arith_mode == D2PC_ARITH_FAST;
-  L.compact = c.filter_mode == D2PC_FILTER_CROP_FINITE;
-  L.scratch = scratch;
-  L.tables = tables;
-  L.ticket = ticket;
   L.epoch = L.compact ? next_epoch(ctx) : 0;
-  L.sm_count = ctx->sm_count;
-  L.rows_per_unit = ctx->rows_per_unit;
-  L.ctas_per_sm = ctx->ctas_per_sm;
-  L.force_scalar = ctx->force_scalar;
-  L.force_generic = ctx->force_generic;
-  L.compact_variant = ctx->compact_variant;
-  L.exact_variant = ctx->exact_variant;
-  L.zero_numer = ctx->zero_numer;
-  L.prefetch_dist = ctx->prefetch_dist;
   CU(ctx, launch_reproject(L, stream, &nl));
   ctx->launches += nl;
   return D2PC_OK;
@@ -667,6 +678,7 @@ int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value) {
   else if (k == "force_park" || k == "compact_variant") ctx->compact_variant = value;
   else if (k == "exact_variant") ctx->exact_variant = value;
   else if (k == "zero_numer") ctx->zero_numer = value;
+  else if (k == "fuse_median") ctx->fuse_median = value;
   else if (k == "prefetch_dist") ctx->prefetch_dist = value;
   else if (k == "median_ksize") {
     if (value < 1 || value > 15 || !(value & 1)) return D2PC_ERR_INVALID_ARG;

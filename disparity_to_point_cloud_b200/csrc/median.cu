@@ -17,6 +17,8 @@
 
 #include <cstdint>
 
+#include "reproject_math.cuh"
+
 namespace d2pc {
 namespace {
 
@@ -32,6 +34,11 @@ struct MedianArgs {
   int ox0, oy0, ow, oh;  // output region (inside the image); dst is addressed with image coordinates
   int strip_rows, n_colblk, n_strip;
   uint32_t units_per_frame, total_units;
+  // fused DisparityCb (kFuse): the median goes straight through cpp:61-75 instead of to dst
+  float4 *points;
+  size_t points_frame_stride;  // in points
+  float scale;
+  QParams Q;
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
@@ -47,7 +54,11 @@ __device__ __forceinline__ void bump_if_below(int &below, uint32_t off, uint32_t
   asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.s32 %0, %0, %3;\n\t}" : "+r"(below) : "r"(off), "r"(med_off), "n"(kDelta));
 }
 
-template <int K>
+// kFuse: instead of storing the median byte, finish the reference's callback for that pixel -- x 1/8 (cpp:61),
+// reprojectImageTo3D with the rectified exact arithmetic (cpp:63-64), PointXYZ{x, y, z, 1.0f} at its crop position
+// (cpp:67-75): a warp's 32 points are one 512-byte store.  The intermediate median image and the second launch of
+// the mono8 callback disappear; the FP64 / conversion work issues in the gaps of this LSU-bound kernel.
+template <int K, bool kFuse>
 __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_constant__ MedianArgs a) {
   constexpr int R = K / 2;
   constexpr int kRank = (K * K) / 2;
@@ -69,6 +80,15 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
     const uint8_t *src = a.src + (size_t)f * a.src_frame_stride;
     uint8_t *dst = a.dst + (size_t)f * a.dst_frame_stride;
     const bool col_ok = (x0 + lane) < (a.ox0 + a.ow);
+    // fused: this lane's column numerator X = (double)(float)(u + q03), for the whole strip
+    double xd = 0.0;
+    bool xslow = false;
+    float4 *points = nullptr;
+    if constexpr (kFuse) {
+      xd = rect_axis_const(x0 + lane, a.Q.q03);
+      xslow = rect_axis_slow(xd) || a.Q.zd_slow;
+      points = a.points + (size_t)f * a.points_frame_stride + (x0 + lane - a.ox0);
+    }
 
     // columns this lane fetches for every ring row (replicate border = clamp)
     const int gx_a = clampi(x0 - R + lane, 0, a.width - 1);
@@ -116,7 +136,18 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
 
     int slot = 0;  // ring slot holding the oldest window row
     for (int y = y_first; y < y_end; ++y) {
-      if (col_ok) dst[(size_t)y * a.dst_step + x0 + lane] = (uint8_t)med;
+      if constexpr (kFuse) {
+        if (col_ok) {
+          const float disp = __fadd_rn(__fmul_rn((float)med, a.scale), 0.0f);  // convertTo(CV_32FC1, 1/8), cpp:61
+          const double yd = rect_axis_const(y, a.Q.q13);
+          bool slow;
+          float4 p = reproject_exact_rectified<true, true>(a.Q, xd, yd, xslow || rect_axis_slow(yd), false, disp, slow);
+          if (__builtin_expect(slow, 0)) p = reproject_exact_slow(a.Q.q, x0 + lane, y, disp);
+          __stcs(points + (size_t)(y - a.oy0) * a.ow, p);
+        }
+      } else {
+        if (col_ok) dst[(size_t)y * a.dst_step + x0 + lane] = (uint8_t)med;
+      }
       if (y + 1 >= y_end) break;
       // prefetch the row entering the window
       const uint8_t *row = src + (size_t)clampi(y + 1 + R, 0, a.height - 1) * a.src_step;
@@ -194,7 +225,8 @@ __global__ void __launch_bounds__(128) median3_net_kernel(const __grid_constant_
 
 template <int K>
 cudaError_t launch_k(const MedianArgs &a, int grid, cudaStream_t s) {
-  median_hist_kernel<K><<<grid, kThreads, 0, s>>>(a);
+  if (a.points) median_hist_kernel<K, true><<<grid, kThreads, 0, s>>>(a);
+  else median_hist_kernel<K, false><<<grid, kThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -217,8 +249,15 @@ cudaError_t launch_median_u8(const MedianLaunch &L, cudaStream_t stream, int *la
   a.oy0 = L.oy0;
   a.ow = L.ow;
   a.oh = L.oh;
+  if (L.points) {
+    if (!L.Q || L.points_stride_bytes % 16 != 0) return cudaErrorInvalidValue;
+    a.points = reinterpret_cast<float4 *>(L.points);
+    a.points_frame_stride = L.points_stride_bytes / 16;
+    a.scale = L.scale;
+    a.Q = *L.Q;
+  }
   if (launches) *launches = 1;
-  if (L.ksize == 3 && L.variant == 0 && L.oh <= 65535 && L.n_frames <= 65535) {
+  if (L.ksize == 3 && L.variant == 0 && !L.points && L.oh <= 65535 && L.n_frames <= 65535) {
     median3_net_kernel<<<dim3((unsigned)((L.ow + 127) / 128), (unsigned)L.oh, L.n_frames), 128, 0, stream>>>(a);
     return cudaGetLastError();
   }

@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "reproject.h"
+
 namespace d2pc {
 
 struct MedianLaunch {
@@ -18,6 +20,14 @@ struct MedianLaunch {
   int strip_rows = 0;  // 0 = automatic
   int variant = 0;     // 0 = per-thread window histogram (Huang; a selection network for ksize 3),
                        // 2 = window histogram for every ksize (test hook)
+  // Fused DisparityCb (cpp:55-75 in one launch): when `points` is set, each median is scaled (cpp:61), reprojected
+  // with the rectified exact arithmetic (reproject_math.cuh) and stored as a PointXYZ at its crop position; `dst` is
+  // not written.  The output region must be the crop (ox0 = oy0 = border).  Only for a Q that takes the plain
+  // rectified path -- ask reproject_fuses_with_median().
+  uint8_t *points = nullptr;  // device: frame f at points + f * points_stride_bytes
+  size_t points_stride_bytes = 0;
+  const QParams *Q = nullptr;
+  float scale = 0.125f;
 };
 
 cudaError_t launch_median_u8(const MedianLaunch &L, cudaStream_t stream, int *launches);

@@ -1034,6 +1034,25 @@ size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t heigh
 // per-column / per-row numerator tables of the rectified path
 size_t reproject_table_bytes(uint32_t width, uint32_t height) { return ((size_t)width + kSegCols + height) * 8 + 64; }
 
+// Which arithmetic a launch takes (host side, from Q and the knobs).
+static int select_math(const ReprojectLaunch &L) {
+  const QParams &Q = *L.Q;
+  // X is exactly zero on an image column (an integral principal point): keep that column straight-line
+  auto zero_column = [&]() {
+    const double c = std::nearbyint(-Q.q03);
+    return c >= 0.0 && c < (double)L.width && (float)(c + Q.q03) == 0.0f;
+  };
+  const bool zero_numer = L.zero_numer > 0 || (L.zero_numer == 0 && zero_column());
+  return L.arith_fast ? kMathFast
+         : (Q.rectified && !L.force_generic
+                ? (Q.q33_zero ? (L.exact_variant == 1 ? kMathRect0M : (zero_numer ? kMathRect0Z : kMathRect0)) : kMathRectW)
+                : kMathGeneric);
+}
+
+bool reproject_fuses_with_median(const ReprojectLaunch &L) {
+  return L.Q && !L.compact && !L.Q->zd_slow && select_math(L) == kMathRect0;
+}
+
 cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int *launches) {
   const long cw = (long)L.width - 2L * L.border, ch = (long)L.height - 2L * L.border;
   if (launches) *launches = 0;
@@ -1069,17 +1088,7 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
                    (L.frame_stride % valign == 0) && ((size_t)L.border * esz % valign == 0) &&
                    (cw % 4 == 0 || L.border >= 3) && !L.force_scalar;
 
-  // X is exactly zero on an image column (an integral principal point): keep that column straight-line
-  auto zero_column = [&]() {
-    const double c = std::nearbyint(-a.Q.q03);
-    return c >= 0.0 && c < (double)L.width && (float)(c + a.Q.q03) == 0.0f;
-  };
-  const bool zero_numer = L.zero_numer > 0 || (L.zero_numer == 0 && zero_column());
-  const int math = L.arith_fast ? kMathFast
-                   : (a.Q.rectified && !L.force_generic
-                          ? (a.Q.q33_zero ? (L.exact_variant == 1 ? kMathRect0M : (zero_numer ? kMathRect0Z : kMathRect0))
-                                          : kMathRectW)
-                          : kMathGeneric);
+  const int math = select_math(L);
   const bool compact = L.compact;
 
   int grid;

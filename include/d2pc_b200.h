@@ -340,6 +340,7 @@ size_t d2pc_serialize_pointcloud2(const d2pc_ctx *ctx, const d2pc_cloud *cloud, 
  *             "prefetch_dist" (L2 prefetch distance in work units / tiles; 0 automatic, < 0 off),
  *             "exact_variant" (0 guarded multiply, 1 Markstein), "zero_numer" (kernel variant that keeps an
  *             exactly-zero X numerator column straight-line: 0 when Q has such a column, 1 always, -1 never),
+ *             "fuse_median" (mono8 callback: 0 one fused median + reproject launch where Q allows, -1 always two),
  *             "force_scalar", "force_generic"
  *   config  : "median_ksize", "border", "offset_x", "offset_y", "fuse_rule", "fuse_median_ksize",
  *             "fuse_crop_left|right|top|bottom" */

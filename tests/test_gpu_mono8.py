@@ -31,9 +31,66 @@ def test_callback_golden_fixtures(ctx):
 
 @pytest.mark.parametrize("w,h,kind", [(752, 480, "s2"), (640, 480, "s1"), (1280, 720, "s2"), (665, 665, "s1"),
                                       (81, 81, "s1"), (131, 203, "s2"), (80, 80, "s1")])
-def test_mono8_callback_bit_exact(ctx, q, w, h, kind):
+@pytest.mark.parametrize("fuse", [0, -1])
+def test_mono8_callback_bit_exact(ctx, q, w, h, kind, fuse):
+    """fuse 0: the default, median + x 1/8 + reproject + pack as ONE launch (the default Q allows it); -1: the
+    two-launch form (median image, then the reprojection kernel) every other Q / filter mode takes."""
     img = synth.s2_scene(h, w, 11) if kind == "s2" else synth.s1_uniform(h, w, 11)
-    assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, q), f"{w}x{h} {kind}")
+    ctx.set_tuning("fuse_median", fuse)
+    try:
+        n0 = ctx.launch_count()
+        assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, q), f"{w}x{h} {kind}")
+        if (w - 80) * (h - 80) > 0:
+            assert ctx.launch_count() - n0 == (1 if fuse == 0 else 2)
+    finally:
+        ctx.set_tuning("fuse_median", 0)
+
+
+def test_fused_callback_other_q_and_knobs(ctx, q):
+    """The fused launch only exists for the plain rectified arithmetic; anything else must quietly take two launches
+    and give the same bytes: median sizes, a Q with an integral principal point (zero-numerator variant), q33 != 0,
+    a generic Q, the Markstein variant, CROP_FINITE.  Plus the fused path itself on bytes whose disparity is 0 (W = +0:
+    +-inf and, on the row v == 240 of the default Q, NaN) and with a narrow border."""
+    import disparity_to_point_cloud_b200 as d2pc
+    img = synth.s2_scene(300, 500, 21)
+    img[120:130, :] = 0
+    img[:, 250] = 0
+    for ks in (5, 11, 15):
+        ctx.set_tuning("median_ksize", ks)
+        try:
+            want = oracle.crop_pack(oracle.reproject_image_to_3d(oracle.convert_u8_f32(oracle.median_blur(img, ks)), q))
+            assert_same_bits(ctx.process_mono8(img), want, f"fused, ksize {ks}")
+        finally:
+            ctx.set_tuning("median_ksize", 11)
+    ctx.set_tuning("border", 2)
+    try:
+        want = oracle.crop_pack(oracle.reproject_image_to_3d(oracle.convert_u8_f32(oracle.median_blur(img, 11)), q), 2)
+        assert_same_bits(ctx.process_mono8(img), want, "fused, border 2 (replicate edge inside the window)")
+    finally:
+        ctx.set_tuning("border", 40)
+    qi = np.array([[1, 0, 0, -250.0], [0, 1, 0, -150.0], [0, 0, 0, 713.5], [0, 0, 1 / 0.09, 0.0]])
+    qw = q.copy()
+    qw[3, 3] = 0.37
+    qg = golden("reproject_golden.npz")["q_generic"]
+    try:
+        for name, qq, knobs in (("integral principal point", qi, {}), ("q33 != 0", qw, {}), ("generic", qg, {}),
+                                ("Markstein", q, {"exact_variant": 1}), ("forced generic", q, {"force_generic": 1})):
+            ctx.set_q(qq)
+            for k, v in knobs.items():
+                ctx.set_tuning(k, v)
+            try:
+                n0 = ctx.launch_count()
+                assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, qq), name)
+                assert ctx.launch_count() - n0 == 2, name
+            finally:
+                for k in knobs:
+                    ctx.set_tuning(k, 0)
+        ctx.set_q(q)
+        ctx.set_filter_mode(d2pc.FILTER_CROP_FINITE)
+        assert_same_bits(ctx.process_mono8(img), oracle.filter_finite(oracle.disparity_cb_mono8(img, q)), "CROP_FINITE")
+    finally:
+        ctx.set_filter_mode(d2pc.FILTER_CROP)
+        ctx.set_q(q)
 
 
 def test_mono8_strided_message(ctx, q):

@@ -146,6 +146,11 @@ def median(argv):
         m = torch.empty_like(d)
         for variant in variants:
             ctx.set_tuning("median_variant", variant)
+            ctx.set_tuning("fuse_median", -1)
+            s_two = t(lambda: ctx.reproject_mono8_device(d.data_ptr(), f, w, h, w, w * h, o.data_ptr(), n * 16), 10, 3)
+            ctx.set_tuning("fuse_median", 0)
+            print(w, h, f, kind, "variant", variant, "callback as two launches: %.1f us/frame  %.1f Gpix/s"
+                  % (s_two / f * 1e6, f * w * h / s_two / 1e9), flush=True)
             s_all = t(lambda: ctx.reproject_mono8_device(d.data_ptr(), f, w, h, w, w * h, o.data_ptr(), n * 16), 10, 3)
             k = min(f, 4)
             s_med = t(lambda: [ctx.median_u8_device(d[i].data_ptr(), w, h, w, m[i].data_ptr(), w, 11) for i in range(k)], 10, 3) / k
