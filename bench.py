@@ -56,7 +56,7 @@ CONFIGS = {
     2: dict(w=752, h=480, entry="mono8", per_step=1000, ring=250,
             workload="752x480 mono8 disparity stream (S2 scene): whole DisparityCb = median 11 + x1/8 + reproject + "
                      "40px crop + XYZ1 pack (BASELINE configs[1])",
-            kernel="median_hist_kernel<11> + reproject_crop_kernel<u8>"),
+            kernel="median_hist_kernel<11, fused>: median + x1/8 + reproject + pack in one launch"),
     3: dict(w=1280, h=720, entry="f32", per_step=64, ring=64,
             workload="1280x720 float32 disparity (S3), batch of 64 frames: reproject + 40px crop + XYZ1 pack "
                      "(BASELINE configs[2])",
@@ -67,8 +67,8 @@ CONFIGS = {
     5: dict(w=1280, h=720, entry="fusion", per_step=256, ring=64,
             workload="depth_map_fusion: four 1280x720 mono8 maps per frame set -> score preprocessing x2, merge, "
                      "median 3, trim -> DisparityCb on the fused 665x665 map (BASELINE configs[4])",
-            kernel="score_tile_kernel x2 + fuse_merge_kernel + median3_net_kernel + median_hist_kernel<11> + "
-                   "reproject_crop_kernel<u8>"),
+            kernel="score_tile_kernel x2 + fuse_merge_kernel + median3_net_kernel + median_hist_kernel<11, fused> "
+                   "(median + x1/8 + reproject + pack)"),
 }
 OFFSETS = (-7, 15)  # launch/depth_map_fusion.launch
 
