@@ -339,9 +339,11 @@ int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_
     M.variant = ctx->median_variant;
     // the whole callback in one launch where the arithmetic allows it (the default Q does): median -> x 1/8 ->
     // reproject -> PointXYZ, no intermediate image
+    bool zero_numer = false;
     const bool fuse = ctx->fuse_median >= 0 && M.ow > 0 && M.oh > 0 && (c.median_ksize > 3 || M.variant != 0) &&
-                      reproject_fuses_with_median(L);
+                      reproject_fuses_with_median(L, &zero_numer);
     if (fuse) {
+      M.zero_numer = zero_numer;
       M.points = d_out;
       M.points_stride_bytes = out_stride;
       M.Q = &ctx->Q;

@@ -38,6 +38,7 @@ struct MedianArgs {
   float4 *points;
   size_t points_frame_stride;  // in points
   float scale;
+  int zero_numer;
   QParams Q;
 };
 
@@ -54,11 +55,13 @@ __device__ __forceinline__ void bump_if_below(int &below, uint32_t off, uint32_t
   asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.s32 %0, %0, %3;\n\t}" : "+r"(below) : "r"(off), "r"(med_off), "n"(kDelta));
 }
 
-// kFuse: instead of storing the median byte, finish the reference's callback for that pixel -- x 1/8 (cpp:61),
+// kFuse != 0: instead of storing the median byte, finish the reference's callback for that pixel -- x 1/8 (cpp:61),
 // reprojectImageTo3D with the rectified exact arithmetic (cpp:63-64), PointXYZ{x, y, z, 1.0f} at its crop position
 // (cpp:67-75): a warp's 32 points are one 512-byte store.  The intermediate median image and the second launch of
 // the mono8 callback disappear; the FP64 / conversion work issues in the gaps of this LSU-bound kernel.
-template <int K, bool kFuse>
+// kFuse: 0 store the median, 1 fused callback, 2 fused callback with zero numerators kept straight-line (the
+// arithmetic of the kMathRect0Z kernels: ~3 % slower, so only for a Q with an integral principal point column).
+template <int K, int kFuse>
 __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_constant__ MedianArgs a) {
   constexpr int R = K / 2;
   constexpr int kRank = (K * K) / 2;
@@ -82,11 +85,12 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
     const bool col_ok = (x0 + lane) < (a.ox0 + a.ow);
     // fused: this lane's column numerator X = (double)(float)(u + q03), for the whole strip
     double xd = 0.0;
-    bool xslow = false;
+    bool xslow = false, xzero = false;
     float4 *points = nullptr;
-    if constexpr (kFuse) {
+    if constexpr (kFuse != 0) {
       xd = rect_axis_const(x0 + lane, a.Q.q03);
-      xslow = rect_axis_slow(xd) || a.Q.zd_slow;
+      xslow = rect_axis_slow_t<kFuse == 2>(xd) || a.Q.zd_slow;
+      xzero = kFuse == 2 && rect_axis_zero(xd);
       points = a.points + (size_t)f * a.points_frame_stride + (x0 + lane - a.ox0);
     }
 
@@ -136,12 +140,13 @@ __global__ void __launch_bounds__(kThreads) median_hist_kernel(const __grid_cons
 
     int slot = 0;  // ring slot holding the oldest window row
     for (int y = y_first; y < y_end; ++y) {
-      if constexpr (kFuse) {
+      if constexpr (kFuse != 0) {
         if (col_ok) {
           const float disp = __fadd_rn(__fmul_rn((float)med, a.scale), 0.0f);  // convertTo(CV_32FC1, 1/8), cpp:61
           const double yd = rect_axis_const(y, a.Q.q13);
           bool slow;
-          float4 p = reproject_exact_rectified<true, true>(a.Q, xd, yd, xslow || rect_axis_slow(yd), false, disp, slow);
+          float4 p = reproject_exact_rectified<true, true, kFuse == 2>(
+              a.Q, xd, yd, xslow || rect_axis_slow_t<kFuse == 2>(yd), xzero || (kFuse == 2 && rect_axis_zero(yd)), disp, slow);
           if (__builtin_expect(slow, 0)) p = reproject_exact_slow(a.Q.q, x0 + lane, y, disp);
           __stcs(points + (size_t)(y - a.oy0) * a.ow, p);
         }
@@ -225,8 +230,9 @@ __global__ void __launch_bounds__(128) median3_net_kernel(const __grid_constant_
 
 template <int K>
 cudaError_t launch_k(const MedianArgs &a, int grid, cudaStream_t s) {
-  if (a.points) median_hist_kernel<K, true><<<grid, kThreads, 0, s>>>(a);
-  else median_hist_kernel<K, false><<<grid, kThreads, 0, s>>>(a);
+  if (a.points && a.zero_numer) median_hist_kernel<K, 2><<<grid, kThreads, 0, s>>>(a);
+  else if (a.points) median_hist_kernel<K, 1><<<grid, kThreads, 0, s>>>(a);
+  else median_hist_kernel<K, 0><<<grid, kThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -254,6 +260,7 @@ cudaError_t launch_median_u8(const MedianLaunch &L, cudaStream_t stream, int *la
     a.points = reinterpret_cast<float4 *>(L.points);
     a.points_frame_stride = L.points_stride_bytes / 16;
     a.scale = L.scale;
+    a.zero_numer = L.zero_numer ? 1 : 0;
     a.Q = *L.Q;
   }
   if (launches) *launches = 1;

@@ -28,6 +28,7 @@ struct MedianLaunch {
   size_t points_stride_bytes = 0;
   const QParams *Q = nullptr;
   float scale = 0.125f;
+  bool zero_numer = false;  // Q has an exactly-zero X numerator column: reproject_fuses_with_median() says so
 };
 
 cudaError_t launch_median_u8(const MedianLaunch &L, cudaStream_t stream, int *launches);

@@ -1049,8 +1049,11 @@ static int select_math(const ReprojectLaunch &L) {
                 : kMathGeneric);
 }
 
-bool reproject_fuses_with_median(const ReprojectLaunch &L) {
-  return L.Q && !L.compact && !L.Q->zd_slow && select_math(L) == kMathRect0;
+bool reproject_fuses_with_median(const ReprojectLaunch &L, bool *zero_numer) {
+  if (!L.Q || L.compact || L.Q->zd_slow) return false;
+  const int math = select_math(L);
+  if (zero_numer) *zero_numer = math == kMathRect0Z;
+  return D2PC_IS_GUARD(math);
 }
 
 cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int *launches) {

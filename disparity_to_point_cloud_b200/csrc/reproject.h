@@ -57,8 +57,8 @@ void make_qparams(const double q[16], QParams *out);
 size_t reproject_scratch_bytes(uint32_t n_frames, uint32_t width, uint32_t height, int border);
 size_t reproject_table_bytes(uint32_t width, uint32_t height);
 cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int *launches);
-// True when this launch would run the plain CROP kernel with the rectified guarded-multiply arithmetic and no
-// zero-numerator column -- the one case median.cu's fused DisparityCb kernel implements.
-bool reproject_fuses_with_median(const ReprojectLaunch &L);
+// True when this launch would run the plain CROP kernel with the rectified guarded-multiply arithmetic (with or
+// without a zero-numerator column) -- the case median.cu's fused DisparityCb kernel implements.
+bool reproject_fuses_with_median(const ReprojectLaunch &L, bool *zero_numer);
 
 }  // namespace d2pc

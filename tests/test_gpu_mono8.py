@@ -48,8 +48,8 @@ def test_mono8_callback_bit_exact(ctx, q, w, h, kind, fuse):
 
 def test_fused_callback_other_q_and_knobs(ctx, q):
     """The fused launch only exists for the plain rectified arithmetic; anything else must quietly take two launches
-    and give the same bytes: median sizes, a Q with an integral principal point (zero-numerator variant), q33 != 0,
-    a generic Q, the Markstein variant, CROP_FINITE.  Plus the fused path itself on bytes whose disparity is 0 (W = +0:
+    and give the same bytes: q33 != 0, a generic Q, the Markstein variant, CROP_FINITE (a Q with an integral principal
+    point stays fused: X == 0 on the column u == 250, Y == 0 on the row v == 150, 0 / 0 where the byte is 0 too).  Plus the fused path itself on bytes whose disparity is 0 (W = +0:
     +-inf and, on the row v == 240 of the default Q, NaN) and with a narrow border."""
     import disparity_to_point_cloud_b200 as d2pc
     img = synth.s2_scene(300, 500, 21)
@@ -73,15 +73,17 @@ def test_fused_callback_other_q_and_knobs(ctx, q):
     qw[3, 3] = 0.37
     qg = golden("reproject_golden.npz")["q_generic"]
     try:
-        for name, qq, knobs in (("integral principal point", qi, {}), ("q33 != 0", qw, {}), ("generic", qg, {}),
-                                ("Markstein", q, {"exact_variant": 1}), ("forced generic", q, {"force_generic": 1})):
+        for name, qq, knobs, launches in (("integral principal point", qi, {}, 1), ("q33 != 0", qw, {}, 2),
+                                          ("integral principal point, ordinary kernels", qi, {"zero_numer": -1}, 1),
+                                          ("generic", qg, {}, 2), ("Markstein", q, {"exact_variant": 1}, 2),
+                                          ("forced generic", q, {"force_generic": 1}, 2)):
             ctx.set_q(qq)
             for k, v in knobs.items():
                 ctx.set_tuning(k, v)
             try:
                 n0 = ctx.launch_count()
                 assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, qq), name)
-                assert ctx.launch_count() - n0 == 2, name
+                assert ctx.launch_count() - n0 == launches, name
             finally:
                 for k in knobs:
                     ctx.set_tuning(k, 0)
