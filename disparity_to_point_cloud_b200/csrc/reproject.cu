@@ -1182,8 +1182,10 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
     // L2 prefetch distance in units (~4100 units are in flight; measured plateau 256-2048)
     a.prefetch_dist = L.prefetch_dist < 0 ? 0 : (L.prefetch_dist > 0 ? L.prefetch_dist : 512);
   }
-  // the generic exact path keeps 16 column products in registers: 4 CTAs per SM (<= 128 registers)
-  const int min_blocks = L.ctas_per_sm > 0 ? L.ctas_per_sm : (math == kMathGeneric && !compact ? 4 : 7);
+  // the generic exact path keeps 16 column products in registers: 4 CTAs per SM (<= 128 registers).  The others:
+  // 6 CTAs (80 registers) beat 7 (72, more spills) by 0.5 % in every sustained and burst A/B of round 2
+  // (profiles/r2_crop_rows_power.txt); 8 (64 registers) is 5 % slower.
+  const int min_blocks = L.ctas_per_sm > 0 ? L.ctas_per_sm : (math == kMathGeneric && !compact ? 4 : 6);
   if (launches) *launches += 1;
 
 #define D2PC_DISPATCH(T)                                                          \
