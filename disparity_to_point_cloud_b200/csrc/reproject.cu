@@ -41,6 +41,26 @@ constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kSegCols = 128;  // crop columns per warp-row: 32 lanes x 4
 
+// n / d for n < 2^31 as one 32 x 32 -> 64 multiply and a shift (d fixed per launch; the hardware has no integer
+// divide, and a unit decode with four of them was a tenth of the CROP kernel's instructions).
+// magic = ceil(2^(32+s) / d), s = ceil(log2 d) - 1: magic < 2^32, and e = magic * d - 2^(32+s) < d gives an exact
+// quotient while n * e < 2^(32+s), i.e. for every n < 2^31.
+struct FastDiv {
+  uint32_t magic, shift;  // shift == 0: d == 1
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{0u, 0u};
+  if (d <= 1) return f;
+  uint32_t s = 0;
+  while ((1ull << (s + 1)) < d) ++s;  // ceil(log2 d) - 1
+  f.shift = 32 + s;
+  f.magic = (uint32_t)(((1ull << f.shift) + d - 1) / d);
+  return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, FastDiv f) {
+  return f.shift == 0u ? n : (uint32_t)(((unsigned long long)n * f.magic) >> f.shift);
+}
+
 struct ReprojArgs {
   const uint8_t *in;
   size_t step, frame_stride;
@@ -50,6 +70,7 @@ struct ReprojArgs {
   int n_frames, width, height, border, cw, ch;
   int rows_per_unit, n_seg, n_rb;
   uint32_t units_per_frame, total_units;
+  FastDiv div_upf, div_nseg;  // CROP kernel: unit -> (frame, row block, segment) without integer divisions
   float scale;
   // compaction
   unsigned long long *tile_desc;
@@ -259,9 +280,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(co
   // one work unit (128 crop columns x rows_per_unit crop rows) per warp; the hardware CTA scheduler balances
   const uint32_t unit = blockIdx.x * kWarpsPerCta + wic;
   if (unit >= a.total_units) return;
-  const uint32_t f = unit / a.units_per_frame;
+  const uint32_t f = fastdiv(unit, a.div_upf);
   const uint32_t rem = unit - f * a.units_per_frame;
-  const int rb = rem / a.n_seg;
+  const int rb = (int)fastdiv(rem, a.div_nseg);
   const int seg = rem - rb * a.n_seg;
   const int c_base = seg * kSegCols;
   const int r_base = rb * a.rows_per_unit;
@@ -270,11 +291,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) reproject_crop_kernel(co
   if constexpr (kVec && sizeof(InT) == 4) {
     // L2 prefetch of the unit a warp launched a fraction of a wave later will read (one 512-byte row per lane)
     if (a.prefetch_dist > 0 && lane < a.rows_per_unit) {
-      const uint64_t u2 = (uint64_t)unit + (uint64_t)a.prefetch_dist;
+      const uint32_t u2 = unit + (uint32_t)a.prefetch_dist;  // total_units < 2^31 and the distance is clamped: no wrap
       if (u2 < a.total_units) {
-        const uint32_t f2 = (uint32_t)(u2 / a.units_per_frame);
-        const uint32_t rem2 = (uint32_t)u2 - f2 * a.units_per_frame;
-        const int rb2 = rem2 / a.n_seg, seg2 = rem2 - rb2 * a.n_seg;
+        const uint32_t f2 = fastdiv(u2, a.div_upf);
+        const uint32_t rem2 = u2 - f2 * a.units_per_frame;
+        const int rb2 = (int)fastdiv(rem2, a.div_nseg), seg2 = rem2 - rb2 * a.n_seg;
         const int row2 = rb2 * a.rows_per_unit + lane;
         const int cols2 = min(kSegCols, ((a.cw - seg2 * kSegCols) + 3) & ~3);
         if (row2 < a.ch)
@@ -1176,11 +1197,13 @@ cudaError_t launch_reproject(const ReprojectLaunch &L, cudaStream_t stream, int 
     a.n_rb = (int)((ch + rb - 1) / rb);
     a.units_per_frame = (uint32_t)a.n_seg * (uint32_t)a.n_rb;
     const uint64_t total = (uint64_t)a.units_per_frame * L.n_frames;
-    if (total > 0xffffffffull) return cudaErrorInvalidValue;
+    if (total >= 0x7fffffffull) return cudaErrorInvalidValue;  // fastdiv's domain (8 M units are 1024 4K frames)
     a.total_units = (uint32_t)total;
+    a.div_upf = make_fastdiv(a.units_per_frame);
+    a.div_nseg = make_fastdiv((uint32_t)a.n_seg);
     grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
     // L2 prefetch distance in units (~4100 units are in flight; measured plateau 256-2048)
-    a.prefetch_dist = L.prefetch_dist < 0 ? 0 : (L.prefetch_dist > 0 ? L.prefetch_dist : 512);
+    a.prefetch_dist = L.prefetch_dist < 0 ? 0 : (L.prefetch_dist > 0 ? std::min(L.prefetch_dist, 1 << 24) : 512);
   }
   // the generic exact path keeps 16 column products in registers: 4 CTAs per SM (<= 128 registers).  The others:
   // 6 CTAs (80 registers) beat 7 (72, more spills) by 0.5 % in every sustained and burst A/B of round 2
