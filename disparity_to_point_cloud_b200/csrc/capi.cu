@@ -98,6 +98,12 @@ struct d2pc_ctx {
   bool force_scalar = false, force_generic = false;
   int compact_variant = 0, exact_variant = 0, prefetch_dist = 0, zero_numer = 0;
   int fuse_median = 0;  // mono8 callback as one fused launch where possible: 0 yes, -1 never (two launches)
+  // CROP clouds written by the kernel straight into the page-locked host buffer (no D2H copy after the kernel; the
+  // transfer overlaps the kernel): 0 = the synchronous single-frame mono8 entries only (the median makes that
+  // kernel long enough to hide: -6..-8 % per call; a float frame's 5 us kernel hides nothing and SM stores cross
+  // PCIe ~15 % slower than the copy engine, so streams and float frames keep the copy), 1 = every CROP submission,
+  // -1 = never
+  int direct_out = 0;
   bool timing = false;  // d2pc_set_timing: slot events carry timestamps
   std::vector<std::pair<uintptr_t, bool>> pin_cache;  // host pointer -> pinned (cudaHostAlloc / cudaHostRegister)?
   uint64_t pin_cache_gen = 0;                         // value of g_host_gen the cache was filled under
@@ -377,7 +383,7 @@ int slot_wait_idle(d2pc_ctx *ctx, Slot &s) {
 }
 
 int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_t h, uint32_t step, bool is_f32,
-                  uint8_t *user_dst = nullptr, size_t user_cap = 0) {
+                  uint8_t *user_dst = nullptr, size_t user_cap = 0, bool sync_call = false) {
   if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return D2PC_ERR_INVALID_ARG;
   const int esz = is_f32 ? 4 : 1;
   int rc = check_frame(ctx, data, w, h, step, esz);
@@ -397,8 +403,20 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   const bool user_pinned = user_dst && reinterpret_cast<uintptr_t>(user_dst) % 16 == 0 && lookup_pinned(ctx, user_dst);
   if ((rc = grow_dev(ctx, s.d_in, d_pitch * h))) return rc;
   if (!is_f32 && ctx->cfg.median_ksize > 1 && (rc = grow_dev(ctx, s.d_med, d_pitch * h))) return rc;
-  if ((rc = grow_dev(ctx, s.d_out, n * 16 + 16))) return rc;
   if (!user_pinned && (rc = grow_pin(ctx, s.h_out, n * 16 + 16))) return rc;
+  // direct output: the kernel's point stores go over PCIe into the page-locked destination while it runs, so a lone
+  // frame no longer pays kernel + copy back to back (CROP only: a compacted cloud's size is not known up front)
+  uint8_t *d_direct = nullptr;
+  if (!compact && n &&
+      (ctx->direct_out > 0 || (ctx->direct_out == 0 && sync_call && !is_f32 && ctx->cfg.median_ksize > 1))) {
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, user_pinned ? user_dst : s.h_out.p, 0) == cudaSuccess &&
+        reinterpret_cast<uintptr_t>(dp) % 16 == 0)
+      d_direct = static_cast<uint8_t *>(dp);
+    else
+      cudaGetLastError();
+  }
+  if (!d_direct && (rc = grow_dev(ctx, s.d_out, n * 16 + 16))) return rc;
   if (compact && ((rc = grow_dev(ctx, s.d_scratch, reproject_scratch_bytes(1, w, h, ctx->cfg.border), true)) ||
                   (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(w, h)))))
     return rc;
@@ -433,14 +451,23 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   CU(ctx, cudaStreamWaitEvent(ctx->s_compute, s.ev_h2d, 0));
   {
     NvtxRange nvtx_k("d2pc kernels");
-    rc = enqueue_kernels(ctx, s.d_in.p, is_f32, 1, w, h, d_pitch, d_pitch * h, s.d_med.p, s.d_out.p, n * 16 + 16,
-                         s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
+    rc = enqueue_kernels(ctx, s.d_in.p, is_f32, 1, w, h, d_pitch, d_pitch * h, s.d_med.p,
+                         d_direct ? d_direct : s.d_out.p, n * 16 + 16, s.d_count, s.d_scratch.p, s.d_tables.p,
+                         s.d_count + 1, ctx->s_compute);
   }
   if (rc) return rc;
   CU(ctx, cudaEventRecord(s.ev_kernel, ctx->s_compute));
 
   // ---- D2H (stream 3)
   NvtxRange nvtx_d2h("d2pc D2H");
+  if (d_direct) {
+    // the cloud is already in host memory when the kernel ends: the slot completes on the compute stream
+    CU(ctx, cudaEventRecord(s.ev_d2h, ctx->s_compute));
+    s.pending = true;
+    s.width = w, s.height = h, s.n_points = n, s.compact = false;
+    s.user_dst = user_dst, s.user_cap = user_cap, s.user_pinned = user_pinned;
+    return D2PC_OK;
+  }
   CU(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_kernel, 0));
   if (compact) {
     // the kept count decides how many bytes travel: fetch it, the payload copy is issued in d2pc_wait
@@ -681,6 +708,7 @@ int d2pc_set_tuning(d2pc_ctx *ctx, const char *key, int value) {
   else if (k == "exact_variant") ctx->exact_variant = value;
   else if (k == "zero_numer") ctx->zero_numer = value;
   else if (k == "fuse_median") ctx->fuse_median = value;
+  else if (k == "direct_out") ctx->direct_out = value;
   else if (k == "prefetch_dist") ctx->prefetch_dist = value;
   else if (k == "median_ksize") {
     if (value < 1 || value > 15 || !(value & 1)) return D2PC_ERR_INVALID_ARG;
@@ -752,23 +780,25 @@ int d2pc_submit_f32_into(d2pc_ctx *ctx, int slot, const float *disp, uint32_t w,
 }
 int d2pc_process_mono8_into(d2pc_ctx *ctx, const uint8_t *data, uint32_t w, uint32_t h, uint32_t step, uint8_t *dst,
                             size_t cap, d2pc_cloud *out) {
-  int rc = d2pc_submit_mono8_into(ctx, 0, data, w, h, step, dst, cap);
+  if (!dst) return D2PC_ERR_INVALID_ARG;
+  int rc = submit_common(ctx, 0, data, w, h, step, false, dst, cap, true);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 int d2pc_process_f32_into(d2pc_ctx *ctx, const float *disp, uint32_t w, uint32_t h, uint32_t step, uint8_t *dst,
                           size_t cap, d2pc_cloud *out) {
-  int rc = d2pc_submit_f32_into(ctx, 0, disp, w, h, step, dst, cap);
+  if (!dst) return D2PC_ERR_INVALID_ARG;
+  int rc = submit_common(ctx, 0, disp, w, h, step, true, dst, cap, true);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 
 int d2pc_process_mono8(d2pc_ctx *ctx, const uint8_t *data, uint32_t w, uint32_t h, uint32_t step, d2pc_cloud *out) {
   if (!out) return D2PC_ERR_INVALID_ARG;
-  int rc = d2pc_submit_mono8(ctx, 0, data, w, h, step);
+  int rc = submit_common(ctx, 0, data, w, h, step, false, nullptr, 0, true);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 int d2pc_process_f32(d2pc_ctx *ctx, const float *disp, uint32_t w, uint32_t h, uint32_t step, d2pc_cloud *out) {
   if (!out) return D2PC_ERR_INVALID_ARG;
-  int rc = d2pc_submit_f32(ctx, 0, disp, w, h, step);
+  int rc = submit_common(ctx, 0, disp, w, h, step, true, nullptr, 0, true);
   return rc ? rc : d2pc_wait(ctx, 0, out);
 }
 

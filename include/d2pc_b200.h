@@ -152,7 +152,9 @@ int d2pc_set_arith_mode(d2pc_ctx *ctx, int arith_mode);
 
 /* Whole DisparityCb (src/disparity_to_point_cloud.cpp:46-92) on one mono8
  * frame in host memory: H2D, median 11, x(1/8), reproject with Q, crop 40,
- * pack {x,y,z,1}, D2H.  Synchronous: `out` is complete on return. */
+ * pack {x,y,z,1}, D2H.  Synchronous: `out` is complete on return.  (In CROP mode the kernel of this call stores
+ * the points straight into the page-locked destination, so the transfer to the host runs while the kernel does
+ * instead of as a copy behind it: tuning key "direct_out".) */
 int d2pc_process_mono8(d2pc_ctx *ctx, const uint8_t *data, uint32_t width, uint32_t height, uint32_t step,
                        d2pc_cloud *out);
 
@@ -193,7 +195,8 @@ int d2pc_process_f32_into(d2pc_ctx *ctx, const float *disp, uint32_t width, uint
  * (waits for the device; call it between frames); after d2pc_wait(slot) d2pc_slot_timing reports where that
  * submission's time went on the device: the spans between the events that chain H2D copy -> kernels -> D2H copy
  * (queueing behind other slots included).  In CROP_FINITE mode d2h_us covers the 4-byte count only (the payload
- * is copied inside d2pc_wait).  The host-side spans of every entry point are also NVTX ranges ("d2pc submit ...",
+ * is copied inside d2pc_wait); where the kernel stores the cloud into host memory itself ("direct_out": the
+ * synchronous mono8 entries) the transfer is part of kernels_us and d2h_us is ~0.  The host-side spans of every entry point are also NVTX ranges ("d2pc submit ...",
  * "d2pc H2D", "d2pc kernels", "d2pc D2H") for Nsight. */
 typedef struct d2pc_timing {
   float h2d_us, kernels_us, d2h_us, total_us;
@@ -341,6 +344,8 @@ size_t d2pc_serialize_pointcloud2(const d2pc_ctx *ctx, const d2pc_cloud *cloud, 
  *             "exact_variant" (0 guarded multiply, 1 Markstein), "zero_numer" (kernel variant that keeps an
  *             exactly-zero X numerator column straight-line: 0 when Q has such a column, 1 always, -1 never),
  *             "fuse_median" (mono8 callback: 0 one fused median + reproject launch where Q allows, -1 always two),
+ *             "direct_out" (CROP clouds stored by the kernel straight into the page-locked destination instead of
+ *             a D2H copy behind the kernel: 0 the synchronous mono8 entries only, 1 every submission, -1 never),
  *             "force_scalar", "force_generic"
  *   config  : "median_ksize", "border", "offset_x", "offset_y", "fuse_rule", "fuse_median_ksize",
  *             "fuse_crop_left|right|top|bottom" */

@@ -251,6 +251,64 @@ def test_caller_supplied_destination(ctx, q):
         reg.free()
 
 
+@pytest.mark.parametrize("direct", [-1, 0, 1])
+def test_direct_output_modes(ctx, q, direct):
+    """direct_out: a CROP cloud is written by the kernel straight into the page-locked host buffer (no D2H copy
+    behind the kernel): 0 = synchronous single-frame mono8 entries only (default), 1 = every CROP submission (float
+    frames, slots, streams), -1 = never.  Same bytes in every mode, every destination kind, nothing written past the cloud."""
+    import disparity_to_point_cloud_b200 as d2pc
+    ctx.set_tuning("direct_out", direct)
+    pin = reg = None
+    try:
+        for (w, h, seed) in [(752, 480, 80), (640, 480, 81), (131, 203, 82), (81, 81, 83), (80, 80, 84)]:
+            img = synth.s2_scene(h, w, seed)
+            d = synth.s3_float(h, w, seed)
+            assert_same_bits(ctx.process_mono8(img), oracle.disparity_cb_mono8(img, q), f"mono8 {w}x{h}")
+            assert_same_bits(ctx.process_f32(d), oracle.disparity_cb_f32(d, q), f"f32 {w}x{h}")
+        h, w = 480, 752
+        img = synth.s2_scene(h, w, 85)
+        want = oracle.disparity_cb_mono8(img, q)
+        nb = want.size
+        pin = d2pc.PinnedArray((nb + 64,), np.uint8)
+        reg = d2pc.RegisteredArray(np.empty(nb + 80, np.uint8))
+        own = np.empty(nb + 64, np.uint8)
+        # a registered buffer that is not 16-byte aligned takes the copy path whatever the mode
+        off = (-reg.array.ctypes.data) % 16 + 4
+        for name, dst in (("pinned", pin.array), ("registered", reg.array[:nb + 64]), ("pageable", own),
+                          ("registered, unaligned", reg.array[off:off + nb + 32])):
+            dst[:] = 0xAB
+            got = ctx.process_into(img, dst)
+            assert_same_bits(got, want, name)
+            assert (dst[nb:] == 0xAB).all(), name
+        # slots and a stream (direct only when direct_out = 1), then the two-launch callback and CROP_FINITE
+        a, b = synth.s2_scene(h, w, 86), synth.s1_uniform(h, w, 87)
+        ctx.submit(0, a, dst=pin.array[:nb])
+        ctx.submit(1, b)
+        assert_same_bits(ctx.wait(1), oracle.disparity_cb_mono8(b, q), "slot 1")
+        assert_same_bits(ctx.wait(0), oracle.disparity_cb_mono8(a, q), "slot 0")
+        frames = d2pc.PinnedArray((6, h, w), np.uint8)
+        for i in range(6):
+            frames.array[i] = synth.s2_scene(h, w, 90 + i)
+        clouds = ctx.process_stream(frames.array)
+        for i in (0, 3, 5):
+            assert_same_bits(clouds[i], oracle.disparity_cb_mono8(frames.array[i], q), f"stream frame {i}")
+        frames.free()
+        ctx.set_tuning("fuse_median", -1)
+        assert_same_bits(ctx.process_mono8(img), want, "two-launch callback")
+        ctx.set_tuning("fuse_median", 0)
+        ctx.set_filter_mode(d2pc.FILTER_CROP_FINITE)
+        assert_same_bits(ctx.process_mono8(img), oracle.filter_finite(want), "CROP_FINITE is never direct")
+        ctx.set_filter_mode(d2pc.FILTER_CROP)
+    finally:
+        ctx.set_tuning("direct_out", 0)
+        ctx.set_tuning("fuse_median", 0)
+        ctx.set_filter_mode(d2pc.FILTER_CROP)
+        if pin:
+            pin.free()
+        if reg:
+            reg.free()
+
+
 def test_per_call_timing(q):
     """d2pc_set_timing / d2pc_slot_timing: the device-side spans of one submission (H2D, kernels, D2H) are positive,
     add up to the total, and the call still produces the same bytes; without timing enabled the query says so."""
@@ -267,8 +325,16 @@ def test_per_call_timing(q):
             assert_same_bits(c.process_mono8(img), want, "timed call")
         t = c.slot_timing(0)
         assert t.points == want.size // 16
+        # a synchronous mono8 call stores its cloud from the kernel (direct_out): the transfer is inside the kernel span
+        assert t.h2d_us > 0 and t.kernels_us > 40 and 0 <= t.d2h_us < 20 and t.total_us < 5000
+        assert abs(t.h2d_us + t.kernels_us + t.d2h_us - t.total_us) < 0.05 * t.total_us + 2
+        c.set_tuning("direct_out", -1)  # the three-stage form: H2D, kernels, D2H copy
+        for _ in range(2):
+            assert_same_bits(c.process_mono8(img), want, "timed call, copy after the kernel")
+        t = c.slot_timing(0)
         assert t.h2d_us > 0 and t.kernels_us > 5 and t.d2h_us > 20 and t.total_us < 5000
         assert abs(t.h2d_us + t.kernels_us + t.d2h_us - t.total_us) < 0.05 * t.total_us + 2
+        c.set_tuning("direct_out", 0)
         c.submit(1, img)
         c.wait(1)
         assert c.slot_timing(1).kernels_us > 5

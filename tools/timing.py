@@ -7,6 +7,7 @@
     python tools/timing.py median                         mono8 callback + median alone, per median variant / strip
     python tools/timing.py score                          MatchingScoreCb1/2 (device entry)
     python tools/timing.py latency                        synchronous per-call latency of the host entry points
+    python tools/timing.py direct [calls]                 A/B of direct_out (kernel writes the cloud into host memory) per call
     python tools/timing.py stream                         end-to-end stream throughput vs pipeline depth
     python tools/timing.py fusion [slots...]              config 5: frame sets / s vs slots, spans of one set, submit cost
     python tools/timing.py numer                          cost of an integral principal point, both kernel variants
@@ -183,7 +184,12 @@ def latency(argv):
         ts.sort()
         return statistics.median(ts) * 1e6, ts[int(0.99 * n)] * 1e6
 
+    # argv[0]: direct_out tuning (-1 = D2H copy after the kernel, 0 = the default: the kernel of a synchronous call
+    # writes the cloud straight into page-locked host memory)
+    direct = int(argv[0]) if argv else 0
     with d2pc.Context() as ctx:
+        ctx.set_tuning("direct_out", direct)
+        print(f"direct_out = {direct}", flush=True)
         for (w, h) in [(640, 480), (752, 480), (1280, 720)]:
             img = synth.s2_scene(h, w, 1)
             d = synth.s3_float(h, w, 1)
@@ -206,6 +212,44 @@ def latency(argv):
                   f"d2pc_process_mono8_into a registered buffer {into[0]:.0f} us (p99 {into[1]:.0f})", flush=True)
 
 
+def direct(argv):
+    """A/B of direct_out for the synchronous entries: the two modes alternate call by call in one process (box noise
+    hits both alike); wall-clock median / p10 / p90 per mode, then the device-side spans of a timed call."""
+    n = int(argv[0]) if argv else 1500
+    with d2pc.Context() as ctx:
+        for (w, h) in [(640, 480), (752, 480), (1280, 720)]:
+            img = synth.s2_scene(h, w, 1)
+            d = synth.s3_float(h, w, 1)
+            for name, fn in (("mono8", lambda: ctx.process_mono8(img, copy=False)), ("f32", lambda: ctx.process_f32(d, copy=False))):
+                ts = {-1: [], 0: []}
+                for i in range(2 * n + 40):
+                    mode = -1 if i % 2 else 0
+                    ctx.set_tuning("direct_out", mode)
+                    t0 = time.perf_counter()
+                    fn()
+                    dt = time.perf_counter() - t0
+                    if i >= 40:
+                        ts[mode].append(dt * 1e6)
+                out = []
+                for mode in (-1, 0):
+                    v = sorted(ts[mode])
+                    out.append(f"direct_out {mode:2d}: median {v[len(v)//2]:6.1f} us (p10 {v[len(v)//10]:6.1f}, p90 {v[9*len(v)//10]:6.1f})")
+                print(f"{w}x{h} {name}: " + "; ".join(out), flush=True)
+            ctx.set_timing(True)
+            for mode in (-1, 0):
+                ctx.set_tuning("direct_out", mode)
+                sp = []
+                for _ in range(50):
+                    ctx.process_mono8(img, copy=False)
+                    t = ctx.slot_timing(0)
+                    sp.append((t.total_us, t.h2d_us, t.kernels_us, t.d2h_us))
+                sp.sort()
+                m = sp[len(sp) // 2]
+                print(f"{w}x{h} mono8 spans, direct_out {mode:2d}: total {m[0]:.1f} us = H2D {m[1]:.1f} + kernels {m[2]:.1f} + D2H {m[3]:.1f}", flush=True)
+            ctx.set_timing(False)
+            ctx.set_tuning("direct_out", 0)
+
+
 def stream(argv):
     for (w, h, dt, nfr) in [(752, 480, np.uint8, 2000), (3840, 2160, np.float32, 128), (1280, 720, np.float32, 1000)]:
         pin = d2pc.PinnedArray((8, h, w), dt)
@@ -213,6 +257,8 @@ def stream(argv):
             pin.array[i] = synth.s2_scene(h, w, 100 + i) if dt == np.uint8 else synth.s3_float(h, w, 100 + i)
         for slots in (2, 3, 4, 6):
             ctx = d2pc.Context(n_slots=slots)
+            if argv:
+                ctx.set_tuning("direct_out", int(argv[0]))  # 1: streamed frames also write their clouds directly
             ctx.process_stream(pin.array, collect=False)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -283,7 +329,7 @@ def fusion(argv):
 
 
 if __name__ == "__main__":
-    cmds = {"crop": crop, "compact": compact, "generic": generic, "numer": numer, "median": median, "score": score, "latency": latency,
+    cmds = {"crop": crop, "compact": compact, "generic": generic, "numer": numer, "median": median, "score": score, "latency": latency, "direct": direct,
             "stream": stream, "fusion": fusion}
     if len(sys.argv) < 2 or sys.argv[1] not in cmds:
         raise SystemExit(__doc__)
