@@ -221,17 +221,18 @@ def direct(argv):
             img = synth.s2_scene(h, w, 1)
             d = synth.s3_float(h, w, 1)
             for name, fn in (("mono8", lambda: ctx.process_mono8(img, copy=False)), ("f32", lambda: ctx.process_f32(d, copy=False))):
-                ts = {-1: [], 0: []}
-                for i in range(2 * n + 40):
-                    mode = -1 if i % 2 else 0
+                modes = [-1, 0]  # direct_out
+                ts = {m: [] for m in modes}
+                for i in range(len(modes) * n + 60):
+                    mode = modes[i % len(modes)]
                     ctx.set_tuning("direct_out", mode)
                     t0 = time.perf_counter()
                     fn()
                     dt = time.perf_counter() - t0
-                    if i >= 40:
+                    if i >= 60:
                         ts[mode].append(dt * 1e6)
                 out = []
-                for mode in (-1, 0):
+                for mode in modes:
                     v = sorted(ts[mode])
                     out.append(f"direct_out {mode:2d}: median {v[len(v)//2]:6.1f} us (p10 {v[len(v)//10]:6.1f}, p90 {v[9*len(v)//10]:6.1f})")
                 print(f"{w}x{h} {name}: " + "; ".join(out), flush=True)
