@@ -1254,14 +1254,23 @@ int d2pc_fuse_then_process(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, 
   const uint32_t fw = (uint32_t)g.out_w, fh = (uint32_t)g.out_h;
   const uint64_t n = crop_points(fw, fh, ctx->cfg.border);
   const bool compact = ctx->cfg.filter_mode == D2PC_FILTER_CROP_FINITE;
-  if ((rc = grow_dev(ctx, s.d_med, (size_t)fw * fh)) || (rc = grow_dev(ctx, s.d_out, n * 16 + 16)) ||
-      (rc = grow_pin(ctx, s.h_out, n * 16 + 16)))
-    return rc;
+  if ((rc = grow_dev(ctx, s.d_med, (size_t)fw * fh)) || (rc = grow_pin(ctx, s.h_out, n * 16 + 16))) return rc;
+  // a synchronous call: the callback kernel stores the CROP cloud straight into the pinned buffer (see submit_common)
+  uint8_t *d_direct = nullptr;
+  if (!compact && n && ctx->direct_out >= 0 && ctx->cfg.median_ksize > 1) {
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, s.h_out.p, 0) == cudaSuccess && reinterpret_cast<uintptr_t>(dp) % 16 == 0)
+      d_direct = static_cast<uint8_t *>(dp);
+    else
+      cudaGetLastError();
+  }
+  if (!d_direct && (rc = grow_dev(ctx, s.d_out, n * 16 + 16))) return rc;
   if (compact && ((rc = grow_dev(ctx, s.d_scratch, reproject_scratch_bytes(1, fw, fh, ctx->cfg.border), true)) ||
                   (rc = grow_dev(ctx, s.d_tables, reproject_table_bytes(fw, fh)))))
     return rc;
-  rc = enqueue_kernels(ctx, ctx->d_fused.p, false, 1, fw, fh, fw, (size_t)fw * fh, s.d_med.p, s.d_out.p, n * 16 + 16,
-                       s.d_count, s.d_scratch.p, s.d_tables.p, s.d_count + 1, ctx->s_compute);
+  rc = enqueue_kernels(ctx, ctx->d_fused.p, false, 1, fw, fh, fw, (size_t)fw * fh, s.d_med.p,
+                       d_direct ? d_direct : s.d_out.p, n * 16 + 16, s.d_count, s.d_scratch.p, s.d_tables.p,
+                       s.d_count + 1, ctx->s_compute);
   if (rc) return rc;
   uint64_t kept = n;
   if (compact) {
@@ -1269,7 +1278,8 @@ int d2pc_fuse_then_process(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, 
     CU(ctx, cudaStreamSynchronize(ctx->s_compute));
     kept = n ? s.h_count[0] : 0;
   }
-  if (kept) CU(ctx, cudaMemcpyAsync(s.h_out.p, s.d_out.p, kept * 16, cudaMemcpyDeviceToHost, ctx->s_compute));
+  if (kept && !d_direct)
+    CU(ctx, cudaMemcpyAsync(s.h_out.p, s.d_out.p, kept * 16, cudaMemcpyDeviceToHost, ctx->s_compute));
   CU(ctx, cudaStreamSynchronize(ctx->s_compute));
   if (ctx->cfg.verbose) printf("Cloud size: %llu\n", (unsigned long long)kept);
   fill_cloud(ctx, s.h_out.p, kept, compact, out);

@@ -115,11 +115,17 @@ def test_bad_geometry_is_an_error(ctx):
         ctx.set_tuning("offset_y", 15)
 
 
-def test_config5_fuse_then_reproject(ctx):
-    """BASELINE config 5: four 1280x720 maps -> 665x665 fused -> DisparityCb -> 585x585 points."""
+@pytest.mark.parametrize("direct", [0, -1])
+def test_config5_fuse_then_reproject(ctx, direct):
+    """BASELINE config 5: four 1280x720 maps -> 665x665 fused -> DisparityCb -> 585x585 points (direct 0: the
+    callback kernel stores the cloud into the pinned buffer itself; -1: device buffer + D2H copy)."""
     q = golden("q_golden.npz")["q"][0]
     d1, d2, s1, s2 = _four(720, 1280, 6)
-    got = ctx.fuse_then_process(d1, d2, s1, s2)
+    ctx.set_tuning("direct_out", direct)
+    try:
+        got = ctx.fuse_then_process(d1, d2, s1, s2)
+    finally:
+        ctx.set_tuning("direct_out", 0)
     assert got.size == 342225 * 16
     fused, _ = oracle.fuse(d1, d2, s1, s2, -7, 15)
     assert fused.shape == (665, 665)

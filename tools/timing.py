@@ -249,6 +249,23 @@ def direct(argv):
                 print(f"{w}x{h} mono8 spans, direct_out {mode:2d}: total {m[0]:.1f} us = H2D {m[1]:.1f} + kernels {m[2]:.1f} + D2H {m[3]:.1f}", flush=True)
             ctx.set_timing(False)
             ctx.set_tuning("direct_out", 0)
+    # the synchronous config-5 call: four 1280x720 frames -> fused 665x665 map -> DisparityCb
+    with d2pc.Context(offset_x=-7, offset_y=15) as ctx:
+        four = [synth.s2_scene(720, 1280, 5 + i) for i in range(4)]
+        ts = {-1: [], 0: []}
+        for i in range(2 * 300 + 20):
+            mode = -1 if i % 2 else 0
+            ctx.set_tuning("direct_out", mode)
+            cl = d2pc.Cloud()
+            t0 = time.perf_counter()
+            rc = d2pc.lib().d2pc_fuse_then_process(ctx._h, *(a.ctypes.data for a in four), 1280, 720, 1280, ctypes.byref(cl))
+            dt = time.perf_counter() - t0
+            assert rc == 0 and cl.width == 585 * 585
+            if i >= 20:
+                ts[mode].append(dt * 1e6)
+        for mode in (-1, 0):
+            v = sorted(ts[mode])
+            print(f"fuse_then_process 4 x 1280x720, direct_out {mode:2d}: median {v[len(v)//2]:6.1f} us (p10 {v[len(v)//10]:6.1f}, p90 {v[9*len(v)//10]:6.1f})", flush=True)
 
 
 def stream(argv):
