@@ -165,3 +165,71 @@ def test_fuzz_against_oracle(env):
     if N_CASES >= 80:
         assert len(seen) >= 12, seen  # the draw really spreads over entries x Q forms x filter modes
     print(f"fuzz: {N_CASES} cases from seed {SEED0}, {len(seen)} (entry, Q, filter) classes")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# depth_map_fusion: merge (rotate / crop / rule / median 3 / trim), geometry errors, score chain, fused -> cloud
+# ---------------------------------------------------------------------------------------------------------------
+N_FUSION = int(os.environ.get("D2PC_FUZZ_FUSION_CASES", "60"))
+
+
+@pytest.fixture(scope="module")
+def fctx():
+    import disparity_to_point_cloud_b200 as d2pc
+    with d2pc.Context(offset_x=-7, offset_y=15) as c:
+        yield d2pc, c
+
+
+def _fusion_case(case, fctx):
+    d2pc, ctx = fctx
+    rng = np.random.default_rng(SEED0 + 500000 + case)
+    w, h = int(rng.integers(90, 520)), int(rng.integers(90, 420))
+    ox, oy = int(rng.integers(-40, 41)), int(rng.integers(-40, 41))
+    if rng.random() < 0.08:
+        ox = int(rng.integers(-300, 300))  # often leaves the image: cv::Mat::operator() would throw in the reference
+    rule = int(rng.choice([0, 0, 0, 1, 2, 3, 4, 5, 6, 7]))
+    d1, d2, s1, s2 = (_draw_u8(rng, h, w) for _ in range(4))
+    if rng.random() < 0.5:  # correlated maps: d2 is d1 seen by the rotated camera, plus noise
+        d2 = np.ascontiguousarray(np.rot90(np.resize(d1, (w, h)), 1))
+        d2 = np.clip(d2.astype(np.int32) + rng.integers(-6, 7, d2.shape), 0, 255).astype(np.uint8)
+    desc = dict(case=case, w=w, h=h, ox=ox, oy=oy, rule=rule)
+    ctx.set_tuning("offset_x", ox)
+    ctx.set_tuning("offset_y", oy)
+    ctx.set_tuning("fuse_rule", rule)
+    try:
+        try:
+            of, oc = oracle.fuse(d1, d2, s1, s2, ox, oy, mode=rule)
+        except ValueError:
+            with pytest.raises(d2pc.D2pcError) as e:
+                ctx.fuse(d1, d2, s1, s2)
+            assert e.value.status == -7, desc
+            return "geometry"
+        fused, combined = ctx.fuse(d1, d2, s1, s2)
+        assert fused.shape == of.shape and fused.tobytes() == of.tobytes(), desc
+        assert combined.tobytes() == oc.tobytes(), desc
+        # the score chain of both callbacks for this geometry
+        rc1, r1 = oracle.crop_to_square(w, h, ox, oy, oy)
+        rc2, r2 = oracle.crop_to_square(h, w, -ox, -oy, oy)
+        if rc1 == 0 and rc2 == 0 and r1[2] > 0:
+            p1, p2 = ctx.preprocess_score(s1, 1), ctx.preprocess_score(s2, 2)
+            assert p1.tobytes() == oracle.score_preprocess(s1, r1, False).tobytes(), ("score 1", desc)
+            assert p2.tobytes() == oracle.score_preprocess(oracle.rotate_cw(s2), r2, True).tobytes(), ("score 2", desc)
+        # fused map -> DisparityCb without leaving the device (config 5), default rule only to bound the run time
+        if rule == 0 and of.shape[0] > 0 and of.shape[1] > 0:
+            q = ctx.get_q()
+            got = ctx.fuse_then_process(d1, d2, s1, s2)
+            assert got.tobytes() == oracle.disparity_cb_mono8(of, q).tobytes(), ("fuse_then_process", desc)
+        return "ok"
+    finally:
+        ctx.set_tuning("offset_x", -7)
+        ctx.set_tuning("offset_y", 15)
+        ctx.set_tuning("fuse_rule", 0)
+
+
+def test_fuzz_fusion_against_oracle(fctx):
+    outcomes = {}
+    for case in range(N_FUSION):
+        r = _fusion_case(case, fctx)
+        outcomes[r] = outcomes.get(r, 0) + 1
+    assert outcomes.get("ok", 0) > 0
+    print(f"fusion fuzz: {N_FUSION} cases from seed {SEED0}: {outcomes}")
