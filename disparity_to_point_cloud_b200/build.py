@@ -74,21 +74,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
 HARNESS = os.path.join(os.path.dirname(HERE), "tools", "d2pc_offline")
 
 
-def build_harness(force: bool = False) -> str:
-    """C++ offline harness over the node classes of include/d2pc_b200/nodes.hpp (g++, links libd2pc_b200.so)."""
+def build_harness(force: bool = False, sanitize: bool = False) -> str:
+    """C++ offline harness over the node classes of include/d2pc_b200/nodes.hpp (g++, links libd2pc_b200.so).
+    sanitize: the same harness under -fsanitize=address,undefined (the host side of the
+    drop-in -- topic bus, launch-file parser, wire (de)serialisation, node classes -- runs under ASan / UBSan)."""
     src = os.path.join(os.path.dirname(HERE), "tools", "d2pc_offline.cpp")
+    out = HARNESS + ("_asan" if sanitize else "")
     deps = [src, LIB] + [os.path.join(INCLUDE, "d2pc_b200", f) for f in os.listdir(os.path.join(INCLUDE, "d2pc_b200"))]
     deps.append(os.path.join(INCLUDE, "d2pc_b200.h"))
-    if not force and os.path.exists(HARNESS) and os.path.getmtime(HARNESS) >= max(os.path.getmtime(d) for d in deps):
-        return HARNESS
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", INCLUDE, src, "-o", HARNESS, "-L", HERE, "-ld2pc_b200",
-           "-Wl,-rpath,$ORIGIN/../disparity_to_point_cloud_b200"]
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(d) for d in deps):
+        return out
+    flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+             "-fno-omit-frame-pointer"] if sanitize else ["-O2"]
+    cmd = ["g++", "-std=c++17", "-Wall"] + flags + ["-I", INCLUDE, src, "-o", out, "-L", HERE, "-ld2pc_b200",
+                                                    "-Wl,-rpath,$ORIGIN/../disparity_to_point_cloud_b200"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"harness build failed:\n{r.stdout}\n{r.stderr}")
-    return HARNESS
+    return out
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_harness(force="--force" in sys.argv))
+    print(build_harness(force="--force" in sys.argv, sanitize=True))

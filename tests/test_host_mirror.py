@@ -144,3 +144,61 @@ def _score_like(rng, h, w):
     a[rng.integers(0, h, 6), :] = 250
     a[:, rng.integers(0, w, 6)] = 3
     return a
+
+
+# ---- the host side of the drop-in under AddressSanitizer / UBSan --------------------------
+ASAN_ENV = dict(os.environ, ASAN_OPTIONS="protect_shadow_gap=0:detect_leaks=0:abort_on_error=1",
+                UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+
+
+@pytest.fixture(scope="module")
+def harness_asan():
+    from disparity_to_point_cloud_b200 import build
+    build.build()
+    return build.build_harness(sanitize=True)
+
+
+def test_wire_selftest_under_sanitizers(harness_asan, tmp_path):
+    out = tmp_path / "wire.bin"
+    r = subprocess.run([harness_asan, "wire", str(out)], env=ASAN_ENV, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert out.read_bytes() == oracle.serialize_pointcloud2(np.arange(32, dtype=np.uint8), seq=7, sec=11, nsec=13)
+
+
+@pytest.mark.gpu
+def test_node_classes_under_sanitizers(harness, harness_asan, tmp_path):
+    """Both node classes through their whole life (launch-file parsing, subscriptions, callbacks, the registered
+    message buffer the kernel writes into, publication, serialisation, destruction) under ASan + UBSan: clean exit
+    and the same bytes as the plain harness -- node 1 on a 752x480 frame, the fusion node on a 16-callback
+    sequence."""
+    img = synth.s2_scene(480, 752, 44)
+    raw = tmp_path / "in.raw"
+    raw.write_bytes(img.tobytes())
+    outs = {}
+    for name, exe in (("plain", harness), ("asan", harness_asan)):
+        out = tmp_path / f"cloud_{name}.bin"
+        r = subprocess.run([exe, "node1", os.path.join(ROOT, "launch", "d2pcloud.launch"), "752", "480", str(raw), str(out),
+                            "1700000001", "7"], env=ASAN_ENV, capture_output=True, text=True)
+        assert r.returncode == 0, (name, r.stderr[-3000:])
+        outs[name] = out.read_bytes()
+    assert outs["plain"] == outs["asan"]
+    q = golden("q_golden.npz")["q"][0]
+    assert outs["asan"] == oracle.serialize_pointcloud2(oracle.disparity_cb_mono8(img, q), seq=0, sec=1700000001, nsec=7)
+
+    rng = np.random.default_rng(5)
+    h, w, lines = 300, 424, []
+    for step, which in enumerate([3, 4, 1, 2, 2, 3, 2, 1, 4, 2, 2, 1, 3, 4, 2, 2]):
+        a = _score_like(rng, h, w) if which in (3, 4) else synth.s2_scene(h, w, 300 + step)
+        p = tmp_path / f"s{step}.raw"
+        p.write_bytes(a.tobytes())
+        lines.append(f"{which} {p} {2000 + step} {step}")
+    script = tmp_path / "script.txt"
+    script.write_text("\n".join(lines) + "\n")
+    logs = {}
+    for name, exe in (("plain", harness), ("asan", harness_asan)):
+        out = tmp_path / f"log_{name}.bin"
+        r = subprocess.run([exe, "fusion-seq", os.path.join(ROOT, "launch", "depth_map_fusion.launch"), str(w), str(h),
+                            str(script), str(out)], env=ASAN_ENV, capture_output=True, text=True)
+        assert r.returncode == 0, (name, r.stderr[-3000:])
+        logs[name] = out.read_bytes()
+    assert len(logs["asan"]) > 0 and logs["plain"] == logs["asan"]
