@@ -91,6 +91,7 @@ struct d2pc_ctx {
   PinBuf h_score[2];
   DevBuf d_color_in, d_color_out, d_color_lut;
   PinBuf h_color;
+  PinBuf h_stage;  // pinned staging of the synchronous fusion entries' pageable inputs (upload_dense)
   bool color_lut_ready = false;
   cudaEvent_t ev_fuse = nullptr;
   // tuning / test hooks
@@ -290,6 +291,25 @@ bool lookup_pinned(d2pc_ctx *ctx, const void *p) {
   return pinned;
 }
 
+// One caller image (w bytes x h rows, `step` apart) into a DENSE device image on `stream`, for the synchronous
+// fusion entries.  Dense rows travel as ONE 1-D copy straight from the caller's memory (page-locked: DMA in place;
+// pageable: the driver's own chunked staging, which beats a memcpy into pinned staging followed by a DMA -- 103 vs
+// 110 us for a 1280x720 score callback).  Padded rows are packed into pinned staging at `stage_off` first (the caller
+// has grown ctx->h_stage and the stream is idle).  What must be avoided is a PITCHED copy from pageable memory, which
+// the driver stages row by row: with 256-byte-pitched device images the 665 x 665 colouriser input took ~250 us
+// that way and a 752-wide score frame 60 us more than it does now.
+int upload_dense(d2pc_ctx *ctx, size_t stage_off, uint8_t *dst, const uint8_t *src, uint32_t w, uint32_t h, size_t step,
+                 cudaStream_t stream) {
+  const size_t bytes = (size_t)w * h;
+  if (step != w) {
+    uint8_t *stage = ctx->h_stage.p + stage_off;
+    for (uint32_t y = 0; y < h; ++y) memcpy(stage + (size_t)y * w, src + (size_t)y * step, w);
+    src = stage;
+  }
+  CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+  return D2PC_OK;
+}
+
 // Enqueue [median] + reproject for one frame batch already on the device.
 int enqueue_kernels(d2pc_ctx *ctx, const uint8_t *d_in, bool is_f32, uint32_t n_frames, uint32_t w, uint32_t h,
                     size_t step, size_t frame_stride, uint8_t *d_med, uint8_t *d_out, size_t out_stride,
@@ -398,6 +418,7 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   // rows that are already 16-byte multiples stay dense on the device: the H2D copy is then one contiguous DMA
   const size_t d_pitch = (row_bytes % 16 == 0) ? row_bytes : align_up(row_bytes, kAlign);
   const uint64_t n = crop_points(w, h, ctx->cfg.border);
+  if (n * 16 > 0xffffffffull) return D2PC_ERR_BAD_DIMS;  // PointCloud2.row_step / width are uint32
   const bool compact = ctx->cfg.filter_mode == D2PC_FILTER_CROP_FINITE;
   if (user_dst && !compact && user_cap < n * 16) return D2PC_ERR_BUFFER_TOO_SMALL;
   const bool user_pinned = user_dst && reinterpret_cast<uintptr_t>(user_dst) % 16 == 0 && lookup_pinned(ctx, user_dst);
@@ -665,6 +686,7 @@ void d2pc_destroy(d2pc_ctx *ctx) {
   free_dev(ctx->d_score_in), free_dev(ctx->d_score_out[0]), free_dev(ctx->d_score_out[1]);
   free_pin(ctx->h_score[0]), free_pin(ctx->h_score[1]);
   free_dev(ctx->d_color_in), free_dev(ctx->d_color_out), free_dev(ctx->d_color_lut), free_pin(ctx->h_color);
+  free_pin(ctx->h_stage);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->ev_fuse) cudaEventDestroy(ctx->ev_fuse);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -908,10 +930,12 @@ static int reproject_device_common(d2pc_ctx *ctx, const void *d_in, bool is_f32,
   if (w == 0 || h == 0 || step < (size_t)w * esz || (n_frames > 1 && frame_stride < step * h))
     return D2PC_ERR_BAD_DIMS;
   const uint64_t n = crop_points(w, h, ctx->cfg.border);
+  if (n * 16 > 0xffffffffull) return D2PC_ERR_BAD_DIMS;  // per-frame counts and PointCloud2.row_step are uint32
   if (reinterpret_cast<uintptr_t>(d_points) % 16 || points_stride % 16 || (n_frames > 1 && points_stride < n * 16))
     return D2PC_ERR_BAD_DIMS;
   const bool compact = ctx->cfg.filter_mode == D2PC_FILTER_CROP_FINITE;
   if (compact && !d_counts) return D2PC_ERR_INVALID_ARG;
+  if (n_frames == 0) return D2PC_OK;  // an empty batch: nothing to launch (and no size below may wrap)
   CU(ctx, cudaSetDevice(ctx->device));
   int rc;
   if (compact) {
@@ -1075,12 +1099,14 @@ int d2pc_fuse_preprocessed_device(d2pc_ctx *ctx, const uint8_t *d_d1, const uint
 static int fuse_upload_and_run(d2pc_ctx *ctx, const uint8_t *const in[4], uint32_t w, uint32_t h, uint32_t step,
                                FuseGeometry *g) {
   int rc;
-  const size_t pitch = align_up(w, kAlign);
+  const size_t pitch = w, fb = (size_t)w * h;  // dense device images
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->s_compute));
+  if ((rc = grow_pin(ctx, ctx->h_stage, 4 * fb))) return rc;
   for (int i = 0; i < 4; ++i) {
-    if ((rc = grow_dev(ctx, ctx->d_fuse_in[i], pitch * h))) return rc;
-    CU(ctx, cudaMemcpy2DAsync(ctx->d_fuse_in[i].p, pitch, in[i], step, w, h, cudaMemcpyHostToDevice, ctx->s_compute));
+    if ((rc = grow_dev(ctx, ctx->d_fuse_in[i], fb)) ||
+        (rc = upload_dense(ctx, i * fb, ctx->d_fuse_in[i].p, in[i], w, h, step, ctx->s_compute)))
+      return rc;
   }
   const size_t side = (size_t)(w < h ? w : h);
   if ((rc = grow_dev(ctx, ctx->d_fused, side * side)) || (rc = grow_dev(ctx, ctx->d_combined, side * side)))
@@ -1159,14 +1185,14 @@ int d2pc_preprocess_score(d2pc_ctx *ctx, const uint8_t *score, uint32_t w, uint3
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->s_compute));
   int rc;
-  const size_t pitch = align_up(w, kAlign);
+  const size_t pitch = w;  // dense device image
   const size_t side = (size_t)(w < h ? w : h);
   DevBuf &d_out = ctx->d_score_out[which - 1];
   PinBuf &h_out = ctx->h_score[which - 1];
   if ((rc = grow_dev(ctx, ctx->d_score_in, pitch * h)) || (rc = grow_dev(ctx, d_out, side * side)) ||
-      (rc = grow_pin(ctx, h_out, side * side)))
+      (rc = grow_pin(ctx, h_out, side * side)) || (rc = grow_pin(ctx, ctx->h_stage, pitch * h)) ||
+      (rc = upload_dense(ctx, 0, ctx->d_score_in.p, score, w, h, step, ctx->s_compute)))
     return rc;
-  CU(ctx, cudaMemcpy2DAsync(ctx->d_score_in.p, pitch, score, step, w, h, cudaMemcpyHostToDevice, ctx->s_compute));
   int n = 0;
   if ((rc = score_device_impl(ctx, ctx->d_score_in.p, w, h, pitch, which, d_out.p, &n))) return rc;
   CU(ctx, cudaMemcpyAsync(h_out.p, d_out.p, (size_t)n * n, cudaMemcpyDeviceToHost, ctx->s_compute));
@@ -1188,8 +1214,9 @@ int d2pc_fuse_preprocessed(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, 
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->s_compute));
   int rc;
-  const size_t pitch = align_up(w, kAlign), nn = (size_t)g.n * g.n;
+  const size_t pitch = w, nn = (size_t)g.n * g.n;  // dense device images
   const size_t side = (size_t)(w < h ? w : h);
+  if ((rc = grow_pin(ctx, ctx->h_stage, 2 * pitch * h + 2 * nn))) return rc;
   for (int i = 0; i < 2; ++i)
     if ((rc = grow_dev(ctx, ctx->d_fuse_in[i], pitch * h))) return rc;
   for (int i = 2; i < 4; ++i)
@@ -1197,10 +1224,13 @@ int d2pc_fuse_preprocessed(d2pc_ctx *ctx, const uint8_t *d1, const uint8_t *d2, 
   if ((rc = grow_dev(ctx, ctx->d_fused, side * side)) || (rc = grow_dev(ctx, ctx->d_combined, side * side)) ||
       (rc = grow_pin(ctx, ctx->h_fused, (size_t)g.out_w * g.out_h)) || (rc = grow_pin(ctx, ctx->h_combined, nn)))
     return rc;
-  CU(ctx, cudaMemcpy2DAsync(ctx->d_fuse_in[0].p, pitch, d1, step, w, h, cudaMemcpyHostToDevice, ctx->s_compute));
-  CU(ctx, cudaMemcpy2DAsync(ctx->d_fuse_in[1].p, pitch, d2, step, w, h, cudaMemcpyHostToDevice, ctx->s_compute));
-  CU(ctx, cudaMemcpyAsync(ctx->d_fuse_in[2].p, s1c, nn, cudaMemcpyHostToDevice, ctx->s_compute));
-  CU(ctx, cudaMemcpyAsync(ctx->d_fuse_in[3].p, s2c, nn, cudaMemcpyHostToDevice, ctx->s_compute));
+  if ((rc = upload_dense(ctx, 0, ctx->d_fuse_in[0].p, d1, w, h, step, ctx->s_compute)) ||
+      (rc = upload_dense(ctx, pitch * h, ctx->d_fuse_in[1].p, d2, w, h, step, ctx->s_compute)) ||
+      (rc = upload_dense(ctx, 2 * pitch * h, ctx->d_fuse_in[2].p, s1c, (uint32_t)g.n, (uint32_t)g.n, (size_t)g.n,
+                         ctx->s_compute)) ||
+      (rc = upload_dense(ctx, 2 * pitch * h + nn, ctx->d_fuse_in[3].p, s2c, (uint32_t)g.n, (uint32_t)g.n, (size_t)g.n,
+                         ctx->s_compute)))
+    return rc;
   rc = fuse_device_impl(ctx, ctx->d_fuse_in[0].p, ctx->d_fuse_in[1].p, ctx->d_fuse_in[2].p, ctx->d_fuse_in[3].p, w, h,
                         pitch, ctx->d_fused.p, ctx->d_combined.p, nullptr, /*scores_cropped=*/true);
   if (rc) return rc;
@@ -1223,11 +1253,12 @@ int d2pc_colorize_depth(d2pc_ctx *ctx, const uint8_t *gray, uint32_t w, uint32_t
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->s_compute));
   int rc;
-  const size_t pitch = align_up(w, kAlign), px = (size_t)w * h;
+  const size_t pitch = w, px = (size_t)w * h;  // dense device image
   if ((rc = grow_dev(ctx, ctx->d_color_in, pitch * h)) || (rc = grow_dev(ctx, ctx->d_color_out, px * 3)) ||
-      (rc = grow_dev(ctx, ctx->d_color_lut, 1024)) || (rc = grow_pin(ctx, ctx->h_color, px * 3)))
+      (rc = grow_dev(ctx, ctx->d_color_lut, 1024)) || (rc = grow_pin(ctx, ctx->h_color, px * 3)) ||
+      (rc = grow_pin(ctx, ctx->h_stage, px)) ||
+      (rc = upload_dense(ctx, 0, ctx->d_color_in.p, gray, w, h, step, ctx->s_compute)))
     return rc;
-  CU(ctx, cudaMemcpy2DAsync(ctx->d_color_in.p, pitch, gray, step, w, h, cudaMemcpyHostToDevice, ctx->s_compute));
   int nl = 0;
   CU(ctx, launch_colorize(ctx->d_color_in.p, pitch, (int)w, (int)h, ctx->d_color_lut.p, !ctx->color_lut_ready,
                           ctx->d_color_out.p, ctx->s_compute, &nl));

@@ -375,5 +375,12 @@ def test_bad_arguments(ctx):
     assert L.d2pc_set_filter_mode(ctx._h, 7) == -1
     assert L.d2pc_process_mono8_into(ctx._h, img.ctypes.data, 10, 10, 10, None, 0, C.byref(cl)) == -1
     assert L.d2pc_host_register(None, 16) == -1
+    # a frame whose cloud would not fit PointCloud2's uint32 width / row_step is refused before anything is touched
+    assert L.d2pc_process_mono8(ctx._h, img.ctypes.data, 60000, 60000, 60000, C.byref(cl)) == -3
+    assert L.d2pc_reproject_mono8_device(ctx._h, 0x1000, 1, 60000, 60000, 60000, 3600000000, 0x2000, 0, None) == -3
+    # an empty batch is a no-op, not an allocation of (0 - 1) frames
+    n0 = ctx.launch_count()
+    assert L.d2pc_reproject_mono8_device(ctx._h, 0x1000, 0, 752, 480, 752, 752 * 480, 0x2000, 4300800, None) == 0
+    assert ctx.launch_count() == n0
     # d2pc_reproject_f32_device: a float pointer that is not 4-byte aligned is refused, not dereferenced
     assert L.d2pc_reproject_f32_device(ctx._h, 0x1001, 1, 100, 100, 400, 40000, 0x2000, 0, None) == -3

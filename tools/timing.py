@@ -8,6 +8,7 @@
     python tools/timing.py score                          MatchingScoreCb1/2 (device entry)
     python tools/timing.py latency                        synchronous per-call latency of the host entry points
     python tools/timing.py direct [calls]                 A/B of direct_out (kernel writes the cloud into host memory) per call
+    python tools/timing.py callbacks                      per-callback latency of the fusion node's synchronous entries
     python tools/timing.py stream                         end-to-end stream throughput vs pipeline depth
     python tools/timing.py fusion [slots...]              config 5: frame sets / s vs slots, spans of one set, submit cost
     python tools/timing.py numer                          cost of an integral principal point, both kernel variants
@@ -268,6 +269,42 @@ def direct(argv):
             print(f"fuse_then_process 4 x 1280x720, direct_out {mode:2d}: median {v[len(v)//2]:6.1f} us (p10 {v[len(v)//10]:6.1f}, p90 {v[9*len(v)//10]:6.1f})", flush=True)
 
 
+def callbacks(argv):
+    """Per-callback latency of the fusion node's synchronous entries (what include/d2pc_b200/nodes.hpp calls once per
+    message): MatchingScoreCb1/2, publishFusedDepthMap, the colouriser of a debug topic, then DisparityCb on the fused
+    map.  Pageable inputs (a ROS message's data vector), C ABI called directly, wall clock."""
+    L = d2pc.lib()
+
+    def lat(fn, n=300):
+        for _ in range(10):
+            fn()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            rc = fn()
+            ts.append(time.perf_counter() - t0)
+            assert rc == 0
+        ts.sort()
+        return ts[len(ts) // 2] * 1e6
+
+    with d2pc.Context(offset_x=-7, offset_y=15) as ctx:
+        for (w, h) in [(752, 480), (1280, 720)]:
+            d1, d2, s1, s2 = (synth.s2_scene(h, w, 40 + i) for i in range(4))
+            im1, im2, fu, co, col = d2pc.Image(), d2pc.Image(), d2pc.Image(), d2pc.Image(), d2pc.Image()
+            t1 = lat(lambda: L.d2pc_preprocess_score(ctx._h, s1.ctypes.data, w, h, w, 1, ctypes.byref(im1)))
+            t2 = lat(lambda: L.d2pc_preprocess_score(ctx._h, s2.ctypes.data, w, h, w, 2, ctypes.byref(im2)))
+            p1, p2 = im1.array().copy(), im2.array().copy()
+            tf = lat(lambda: L.d2pc_fuse_preprocessed(ctx._h, d1.ctypes.data, d2.ctypes.data, p1.ctypes.data, p2.ctypes.data,
+                                                      w, h, w, ctypes.byref(fu), ctypes.byref(co)))
+            fused = fu.array().copy()
+            fh, fw = fused.shape
+            tc = lat(lambda: L.d2pc_colorize_depth(ctx._h, fused.ctypes.data, fw, fh, fw, ctypes.byref(col)))
+            cl = d2pc.Cloud()
+            td = lat(lambda: L.d2pc_process_mono8(ctx._h, fused.ctypes.data, fw, fh, fw, ctypes.byref(cl)))
+            print(f"{w}x{h}: MatchingScoreCb1 {t1:.0f} us, MatchingScoreCb2 {t2:.0f} us, DisparityCb2 + publishFusedDepthMap "
+                  f"{tf:.0f} us, colorizeDepth({fw}x{fh}) {tc:.0f} us, DisparityCb on the fused map {td:.0f} us", flush=True)
+
+
 def stream(argv):
     for (w, h, dt, nfr) in [(752, 480, np.uint8, 2000), (3840, 2160, np.float32, 128), (1280, 720, np.float32, 1000)]:
         pin = d2pc.PinnedArray((8, h, w), dt)
@@ -347,7 +384,7 @@ def fusion(argv):
 
 
 if __name__ == "__main__":
-    cmds = {"crop": crop, "compact": compact, "generic": generic, "numer": numer, "median": median, "score": score, "latency": latency, "direct": direct,
+    cmds = {"crop": crop, "compact": compact, "generic": generic, "numer": numer, "median": median, "score": score, "latency": latency, "direct": direct, "callbacks": callbacks,
             "stream": stream, "fusion": fusion}
     if len(sys.argv) < 2 or sys.argv[1] not in cmds:
         raise SystemExit(__doc__)
