@@ -415,8 +415,10 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   NvtxRange nvtx_submit(is_f32 ? "d2pc submit f32" : "d2pc submit mono8");
 
   const size_t row_bytes = (size_t)w * esz;
-  // rows that are already 16-byte multiples stay dense on the device: the H2D copy is then one contiguous DMA
-  const size_t d_pitch = (row_bytes % 16 == 0) ? row_bytes : align_up(row_bytes, kAlign);
+  // rows that are already 16-byte multiples stay dense on the device: the H2D copy is then one contiguous DMA.  So do
+  // mono8 rows of any width (the callback kernel reads bytes; a 665-wide fused map is then one DMA instead of a
+  // pitched 2-D copy); float rows that are not 16-byte multiples keep a 256-byte pitch for the vector loads.
+  const size_t d_pitch = (row_bytes % 16 == 0 || !is_f32) ? row_bytes : align_up(row_bytes, kAlign);
   const uint64_t n = crop_points(w, h, ctx->cfg.border);
   if (n * 16 > 0xffffffffull) return D2PC_ERR_BAD_DIMS;  // PointCloud2.row_step / width are uint32
   const bool compact = ctx->cfg.filter_mode == D2PC_FILTER_CROP_FINITE;
