@@ -1335,7 +1335,8 @@ int d2pc_submit_fusion(d2pc_ctx *ctx, int slot, const uint8_t *d1, const uint8_t
   if (rc) return rc;
   // rows that are 16-byte multiples stay dense on the device, so a frame (or a whole contiguous set) is one 1-D DMA:
   // four pitched 2-D copies per set ran at 43 GB/s and bounded the stream at 6.6 k sets/s (one 1-D copy: 9.2 k)
-  const size_t pitch = (w % 16 == 0) ? w : align_up(w, kAlign), frame_bytes = (size_t)w * h, nn = (size_t)g.n * g.n;
+  // (mono8 frames of any width: the fusion kernels read bytes, and a pitched 2-D copy is the slow way in)
+  const size_t pitch = w, frame_bytes = (size_t)w * h, nn = (size_t)g.n * g.n;
   const uint32_t fw = (uint32_t)g.out_w, fh = (uint32_t)g.out_h;
   const uint64_t n = crop_points(fw, fh, c.border);
   const bool compact = c.filter_mode == D2PC_FILTER_CROP_FINITE;

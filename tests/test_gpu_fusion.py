@@ -144,13 +144,14 @@ def _node_pass_oracle(d1, d2, s1, s2, q, preprocess):
     return oracle.disparity_cb_mono8(np.ascontiguousarray(fused), q)
 
 
+@pytest.mark.parametrize("h,w", [(480, 752), (330, 430)])   # rows that are / are not 16-byte multiples
 @pytest.mark.parametrize("preprocess", [True, False])
-def test_fusion_pipeline_slots_and_stream(ctx, preprocess):
+def test_fusion_pipeline_slots_and_stream(ctx, preprocess, h, w):
     """d2pc_submit_fusion / d2pc_process_fusion_stream: whole node passes (the four callbacks + DisparityCb on the
     fused map) overlapped on the slot pipeline; clouds in order, bit-identical to the oracle's node."""
     import disparity_to_point_cloud_b200 as d2pc
     q = golden("q_golden.npz")["q"][0]
-    h, w, n_sets = 480, 752, 5
+    n_sets = 5
     pin = d2pc.PinnedArray((n_sets, 4, h, w), np.uint8)
     rng = np.random.default_rng(77)
     for i in range(n_sets):
