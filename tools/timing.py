@@ -208,9 +208,12 @@ def latency(argv):
             cp = lat(with_copy)
             into = lat(lambda: ctx.process_into(img, reg.array))
             reg.free()
+            own = np.empty(n, np.uint8)
+            into_pageable = lat(lambda: ctx.process_into(img, own))
             print(f"{w}x{h}: process_mono8 median {m8[0]:.0f} us (p99 {m8[1]:.0f}), process_f32 median {f32[0]:.0f} us "
                   f"(p99 {f32[1]:.0f}); mono8 -> message buffer: library cloud + memcpy {cp[0]:.0f} us (p99 {cp[1]:.0f}), "
-                  f"d2pc_process_mono8_into a registered buffer {into[0]:.0f} us (p99 {into[1]:.0f})", flush=True)
+                  f"d2pc_process_mono8_into a registered buffer {into[0]:.0f} us (p99 {into[1]:.0f}), into a pageable "
+                  f"buffer {into_pageable[0]:.0f} us (p99 {into_pageable[1]:.0f})", flush=True)
 
 
 def direct(argv):
