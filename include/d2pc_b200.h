@@ -196,7 +196,8 @@ int d2pc_process_f32_into(d2pc_ctx *ctx, const float *disp, uint32_t width, uint
  * submission's time went on the device: the spans between the events that chain H2D copy -> kernels -> D2H copy
  * (queueing behind other slots included).  In CROP_FINITE mode d2h_us covers the 4-byte count only (the payload
  * is copied inside d2pc_wait); where the kernel stores the cloud into host memory itself ("direct_out": the
- * synchronous mono8 entries) the transfer is part of kernels_us and d2h_us is ~0.  The host-side spans of every entry point are also NVTX ranges ("d2pc submit ...",
+ * synchronous mono8 entries) the transfer is part of kernels_us and d2h_us is ~0; a synchronous call into a pageable
+ * caller buffer moves its cloud inside d2pc_wait, outside these spans.  The host-side spans of every entry point are also NVTX ranges ("d2pc submit ...",
  * "d2pc H2D", "d2pc kernels", "d2pc D2H") for Nsight. */
 typedef struct d2pc_timing {
   float h2d_us, kernels_us, d2h_us, total_us;
