@@ -457,22 +457,20 @@ int submit_common(d2pc_ctx *ctx, int slot, const void *data, uint32_t w, uint32_
   // 1280x720 327 -> 313 us; only padded pageable rows are still packed into pinned staging here)
   const bool pinned = lookup_pinned(ctx, data) || (step == row_bytes && d_pitch == row_bytes);
   if (!pinned) {
-    if ((rc = grow_pin(ctx, s.h_in, row_bytes * h))) return rc;
-    if (step == row_bytes) {
-      memcpy(s.h_in.p, data, row_bytes * h);
-    } else {
-      for (uint32_t y = 0; y < h; ++y)
-        memcpy(s.h_in.p + y * row_bytes, static_cast<const uint8_t *>(data) + (size_t)y * step, row_bytes);
-    }
+    // rows are laid out in the staging buffer with the DEVICE pitch, so what follows is one 1-D DMA (a pitched 2-D
+    // copy is the slow way in, even from pinned memory)
+    if ((rc = grow_pin(ctx, s.h_in, d_pitch * h))) return rc;
+    for (uint32_t y = 0; y < h; ++y)
+      memcpy(s.h_in.p + (size_t)y * d_pitch, static_cast<const uint8_t *>(data) + (size_t)y * step, row_bytes);
     src = s.h_in.p;
-    src_pitch = row_bytes;
+    src_pitch = d_pitch;
   }
   s.timed = ctx->timing && s.ev_start;
   if (s.timed) CU(ctx, cudaEventRecord(s.ev_start, ctx->s_h2d));
   {
     NvtxRange nvtx_h2d("d2pc H2D");
-    if (src_pitch == row_bytes && d_pitch == row_bytes)
-      CU(ctx, cudaMemcpyAsync(s.d_in.p, src, row_bytes * h, cudaMemcpyHostToDevice, ctx->s_h2d));
+    if (src_pitch == d_pitch)  // same layout on both sides (dense, or staged with the device pitch): one 1-D copy
+      CU(ctx, cudaMemcpyAsync(s.d_in.p, src, d_pitch * (h - 1) + row_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
     else
       CU(ctx, cudaMemcpy2DAsync(s.d_in.p, d_pitch, src, src_pitch, row_bytes, h, cudaMemcpyHostToDevice, ctx->s_h2d));
     CU(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
