@@ -5,8 +5,10 @@ and bench.py's cpu_baseline / ``--impl reference`` legs may import this module,
 and only as the checker or the CPU baseline.  The product package
 (disparity_to_point_cloud_b200) never imports it.
 
-Parity pin: see oracle/d2pc_oracle.h -- pinned against cv2 4.13.0 fixtures in
-tests/golden/, because the reference ships no tests and cannot be built here.
+Parity pin: see oracle/d2pc_oracle.h -- OpenCV's arithmetic against cv2 4.13.0
+fixtures in tests/golden/, the reference's own logic against the reference's
+own sources compiled unmodified against stand-in headers (oracle/_ref); the
+reference ships no tests and its build system cannot run here.
 """
 from __future__ import annotations
 
