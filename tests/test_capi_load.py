@@ -89,3 +89,27 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_tuning_keys_documented_in_the_header_match_the_library():
+    """Every integer knob d2pc_set_tuning accepts is listed in include/d2pc_b200.h, and nothing is listed that the
+    library would refuse (no GPU needed: both sides are read from the sources)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "disparity_to_point_cloud_b200", "csrc", "capi.cu")).read()
+    body = src[src.index("int d2pc_set_tuning("):]
+    body = body[: body.index("\n}\n")]
+    accepted = set(re.findall(r'k == "([a-z0-9_]+)"', body))
+    hdr = open(os.path.join(root, "include", "d2pc_b200.h")).read()
+    doc = hdr[hdr.index("Tuning / test hook"): hdr.index("int d2pc_set_tuning(")]
+    documented = set()
+    for m in re.findall(r'"([a-z0-9_|]+)"', doc):
+        if "|" in m:   # "fuse_crop_left|right|top|bottom"
+            head, *rest = m.split("|")
+            stem = head[: head.rindex("_") + 1]
+            documented.add(head)
+            documented.update(stem + r for r in rest)
+        else:
+            documented.add(m)
+    accepted.discard("force_park")  # an alias of compact_variant kept for old scripts
+    assert accepted == documented, (sorted(accepted - documented), sorted(documented - accepted))
